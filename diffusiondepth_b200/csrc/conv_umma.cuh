@@ -1,0 +1,307 @@
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on the 5th-gen tensor cores (tcgen05).
+//
+//   M = 128 output pixels (an 8 x 16 patch of one image), N = COUT, K = 9 taps x CIN.
+//
+// Operands are fp16 hi/lo planes of the fp32 tensors (x = hi + lo, each scaled by a power of two),
+// and every K step issues three MMAs  D += A_lo*B_hi ; D += A_hi*B_lo ; D += A_hi*B_hi  so the
+// fp32 accumulator in TMEM carries ~22 significant bits per product (a single
+// fp16/tf32 pass misses the 1e-3 parity bar after 20 DDIM steps, the 3-pass split matches fp32).
+//
+// Data movement: activations live in HBM as NHWC fp16 planes; a 4-D TMA tensor map {C, W, H, B} with
+// box {BK, 16, 8, 1} fetches the (dy,dx)-shifted patch for each tap straight into the K-major
+// swizzled layout tcgen05 reads, and TMA's out-of-bounds zero fill *is* the conv's zero padding.
+// Weights are pre-packed [tap][COUT][CIN] fp16 hi/lo and fetched by a 3-D map with box {BK, COUT, 1}.
+//
+// Roles (256 threads, persistent over tiles): warp0.lane0 = TMA producer, warp1.lane0 = MMA issuer,
+// warp2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> regs -> +bias -> HBM, GroupNorm partial sums
+// by warp shuffle).  Two TMEM accumulators so tile i's epilogue overlaps tile i+1's MMAs.
+//
+// Replaces: the nn.Conv2d calls inside ScheduledCNNRefine (reference
+// src/model/head/ddim_depth_estimate_res_swin_addHAHI.py:339-359, UpSample_add :321-333).
+#pragma once
+#include "ptx.cuh"
+
+namespace dd {
+
+constexpr int TILE_H = 8;
+constexpr int TILE_W = 16;
+constexpr int TILE_M = TILE_H * TILE_W;  // 128
+
+enum EpiMode : int {
+  EPI_F32_STATS = 0,  // y fp32 NHWC + per-(tile, group) sum / sum-of-squares for the consumer GroupNorm
+  EPI_SPLIT = 1,      // y -> scaled fp16 hi/lo planes (input of the next conv; no norm in between)
+  EPI_F32 = 2         // y fp32 NHWC only
+};
+
+struct ConvArgs {
+  int B, H, W;
+  int tiles_x, tiles_y, num_tiles;
+  const float* bias;       // [COUT]
+  float acc_scale;         // 1 / (act_scale * weight_scale): undoes the power-of-two operand scaling
+  float* y32;              // [B*H*W][COUT]                       (EPI_F32*)
+  float* stats_partial;    // [num_tiles][4][2]                   (EPI_F32_STATS)
+  __half* out_hi;          // [B*H*W][COUT]                       (EPI_SPLIT)
+  __half* out_lo;
+  float split_scale;       // power-of-two scale applied before the fp16 split of the output
+  int* status;             // bit0 set if an fp16 operand would overflow
+};
+
+template <int CIN, int COUT, int BK>
+struct ConvCfg {
+  static_assert(CIN % BK == 0 && (BK == 16 || BK == 32 || BK == 64), "bad K chunk");
+  static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "bad N");
+  static constexpr int KC = CIN / BK;                 // channel chunks per tap
+  static constexpr int K_ITERS = 9 * KC;              // pipeline stages consumed per tile
+  static constexpr int ROW_BYTES = BK * 2;            // one operand row = swizzle span
+  static constexpr int A_BYTES = TILE_M * ROW_BYTES;  // one plane
+  static constexpr int B_BYTES = COUT * ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int SMEM_BUDGET = 200 * 1024;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static_assert(STAGES >= 2, "stage too large");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + scratch*/;
+  static constexpr int TMEM_COLS_RAW = 2 * COUT;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : (TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512)));
+  static constexpr int CH = COUT < 32 ? COUT : 32;    // epilogue column chunk
+  static constexpr int GROUP_CH = COUT / 4;           // GroupNorm(4, COUT)
+};
+
+template <int CIN, int COUT, int BK, int EPI>
+__global__ void __launch_bounds__(256, 1)
+conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const ConvArgs p) {
+  using C = ConvCfg<CIN, COUT, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [2][4 warps][4 groups][2]  (64 floats)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmA_lo);
+    tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&tmB_lo);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int img = tile / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        for (int kc = 0; kc < C::KC; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* s = stage_ptr(stage);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_4d(s, &tmA_hi, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+          tma_load_4d(s + C::A_BYTES, &tmA_lo, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+          tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * BK, 0, tap);
+          tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * BK, 0, tap);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    constexpr uint32_t idesc = umma_idesc_f16(TILE_M, COUT);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t acc_phase = 0;  // bit b = phase of accumulator buffer b
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * COUT);
+      for (int it = 0; it < C::K_ITERS; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa_hi = smem_u32(stage_ptr(stage));
+        const uint32_t sa_lo = sa_hi + C::A_BYTES;
+        const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
+        const uint32_t sb_lo = sb_hi + C::B_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t a_hi = umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES);
+          const uint64_t a_lo = umma_smem_desc(sa_lo + k * 32, C::ROW_BYTES);
+          const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
+          const uint64_t b_lo = umma_smem_desc(sb_lo + k * 32, C::ROW_BYTES);
+          umma_f16(d_tmem, a_lo, b_hi, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+          umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+        if (it == C::K_ITERS - 1) umma_commit(&tfull_bar[buf]);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc_phase ^= (1u << buf);
+      buf ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int r = m >> 4, c = m & 15;
+    uint32_t full_phase = 0;
+    int buf = 0;
+    int par = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int img = tile / (p.tiles_x * p.tiles_y);
+      const int x = tx * TILE_W + c, y = ty * TILE_H + r;
+      const bool valid = (x < p.W) && (y < p.H);
+      const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+
+      mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
+      full_phase ^= (1u << buf);
+      tc_fence_after();
+
+      float tsum[4] = {0.f, 0.f, 0.f, 0.f}, tsq[4] = {0.f, 0.f, 0.f, 0.f};
+      bool overflow = false;
+#pragma unroll
+      for (int ci = 0; ci < COUT / C::CH; ++ci) {
+        const int ch0 = ci * C::CH;
+        float v[C::CH];
+        {
+          const uint32_t taddr =
+              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * COUT + ch0);
+          if constexpr (C::CH == 32) {
+            uint32_t rr[32];
+            tmem_ld_32x32(taddr, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+          } else {
+            uint32_t rr[16];
+            tmem_ld_32x16(taddr, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < C::CH; ++j) v[j] = fmaf(v[j], p.acc_scale, __ldg(p.bias + ch0 + j));
+
+        if constexpr (EPI == EPI_F32_STATS) {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < C::CH; ++j) {
+              const int g = (ch0 + j) / C::GROUP_CH;  // compile-time: both loops are fully unrolled
+              tsum[g] += v[j];
+              tsq[g] = fmaf(v[j], v[j], tsq[g]);
+            }
+          }
+        }
+
+        if (valid) {
+          if constexpr (EPI == EPI_F32_STATS || EPI == EPI_F32) {
+            float4* dst = reinterpret_cast<float4*>(p.y32 + pix * COUT + ch0);
+#pragma unroll
+            for (int j = 0; j < C::CH / 4; ++j)
+              dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            __align__(16) __half hi[C::CH];
+            __align__(16) __half lo[C::CH];
+#pragma unroll
+            for (int j = 0; j < C::CH; ++j) {
+              const float s = v[j] * p.split_scale;
+              overflow |= (fabsf(s) > 60000.f);
+              hi[j] = __float2half_rn(s);
+              lo[j] = __float2half_rn(s - __half2float(hi[j]));
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * COUT + ch0);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * COUT + ch0);
+#pragma unroll
+            for (int j = 0; j < C::CH / 8; ++j) {
+              dh[j] = reinterpret_cast<const uint4*>(hi)[j];
+              dl[j] = reinterpret_cast<const uint4*>(lo)[j];
+            }
+          }
+        }
+      }
+      // accumulator fully drained -> hand the TMEM buffer back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+
+      if constexpr (EPI == EPI_F32_STATS) {
+        // warp tree -> smem -> 8 threads combine the 4 warps in fixed order (deterministic)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float s = tsum[g], s2 = tsq[g];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (lane == 0) {
+            red[((par * 4 + q) * 4 + g) * 2 + 0] = s;
+            red[((par * 4 + q) * 4 + g) * 2 + 1] = s2;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        const int e = threadIdx.x - 128;                // 0..127
+        if (e < 8) {
+          const int g = e >> 1, which = e & 1;
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) t += red[((par * 4 + w) * 4 + g) * 2 + which];
+          p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + which] = t;
+        }
+        par ^= 1;  // double-buffered scratch: one barrier per tile is enough
+      }
+      if constexpr (EPI == EPI_SPLIT) {
+        if (overflow) atomicOr(p.status, 1);
+      }
+      buf ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+}  // namespace dd

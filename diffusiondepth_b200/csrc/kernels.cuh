@@ -1,0 +1,512 @@
+// Everything on the hot path that is not the tensor-core convolution: layout changes at the ABI
+// boundary, the fp16 hi/lo split, GroupNorm finalize/apply (+ReLU, + condition injection), the collapsed
+// DDIM update, the fused depth-latent decoder and an fp32 CUDA-core convolution used for validation.
+// All activations are NHWC inside the engine.
+#pragma once
+#include "conv_umma.cuh"
+
+namespace dd {
+
+__device__ __forceinline__ void split_f16(float v, float scale, __half& hi, __half& lo, bool& overflow) {
+  const float s = v * scale;
+  overflow |= (fabsf(s) > 60000.f);
+  hi = __float2half_rn(s);
+  lo = __float2half_rn(s - __half2float(hi));
+}
+
+// ------------------------------------------------------------------ NCHW <-> NHWC
+// in [B][C][P] -> out [B][P][C]  (32x32 smem transpose; P = H*W)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int P) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + static_cast<size_t>(b) * C * P;
+  float* dst = out + static_cast<size_t>(b) * C * P;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    t[i][threadIdx.x] = (c < C && pp < P) ? src[static_cast<size_t>(c) * P + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    if (pp < P && c < C) dst[static_cast<size_t>(pp) * C + c] = t[threadIdx.x][i];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int P) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + static_cast<size_t>(b) * C * P;
+  float* dst = out + static_cast<size_t>(b) * C * P;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (pp < P && c < C) ? src[static_cast<size_t>(pp) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    if (c < C && pp < P) dst[static_cast<size_t>(c) * P + pp] = t[threadIdx.x][i];
+  }
+}
+
+// fp32 NHWC -> scaled fp16 hi/lo planes (n elements, vectorised by 4)
+__global__ void split_planes_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    size_t n4, float scale, int* status) {
+  bool ov = false;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __align__(8) __half h[4];
+    __align__(8) __half l[4];
+    split_f16(v.x, scale, h[0], l[0], ov);
+    split_f16(v.y, scale, h[1], l[1], ov);
+    split_f16(v.z, scale, h[2], l[2], ov);
+    split_f16(v.w, scale, h[3], l[3], ov);
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(l);
+  }
+  if (ov) atomicOr(status, 1);
+}
+
+// ------------------------------------------------------------------ weight pre-pack
+// w [COUT][CIN][3][3] fp32 -> hi/lo fp16 [tap][COUT][CIN] (scaled) and fp32 [tap][CIN][COUT] (SIMT path)
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo,
+                                        float* __restrict__ w_simt, int cout, int cin, float scale) {
+  const int n = cout * cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9, ci = (i / 9) % cin, co = i / (9 * cin);
+    const float v = w[i];
+    const float s = v * scale;
+    const __half h = __float2half_rn(s);
+    const size_t o = (static_cast<size_t>(tap) * cout + co) * cin + ci;
+    hi[o] = h;
+    lo[o] = __float2half_rn(s - __half2float(h));
+    w_simt[(static_cast<size_t>(tap) * cin + ci) * cout + co] = v;
+  }
+}
+__global__ void absmax_kernel(const float* __restrict__ w, int n, float* __restrict__ out) {
+  __shared__ float sm[256];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+
+// ------------------------------------------------------------------ GroupNorm(4, C) finalize
+// partial [tiles_total][4][2] (fp32 sums over one 128-pixel tile) -> mean/rstd per (image, group).
+// Combined in fp64 in a fixed order (deterministic).
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int tiles_per_img, double inv_count, float eps,
+                                   float* __restrict__ mean_rstd /* [B][4][2] */) {
+  const int b = blockIdx.x >> 2, g = blockIdx.x & 3;
+  double s = 0.0, s2 = 0.0;
+  for (int t = threadIdx.x; t < tiles_per_img; t += blockDim.x) {
+    const float* q = partial + (static_cast<size_t>(b) * tiles_per_img + t) * 8 + g * 2;
+    s += static_cast<double>(q[0]);
+    s2 += static_cast<double>(q[1]);
+  }
+  __shared__ double sh[2][32];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sh[0][warp] = s;
+    sh[1][warp] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, a2 = 0.0;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) {
+      a += sh[0][w];
+      a2 += sh[1][w];
+    }
+    const double mean = a * inv_count;
+    double var = a2 * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_rstd[(b * 4 + g) * 2 + 0] = static_cast<float>(mean);
+    mean_rstd[(b * 4 + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm apply + ReLU (+ condition) -> fp16 planes
+// COND: 0 none, 1 add cond at the same resolution (Res head, reference ddim_depth_estimate_res.py:340),
+//       2 add bilinear-upsampled cond, align_corners=True (Swin head UpSample_add, ..._swin_addHAHI.py:331-333);
+// in both cases the per-image time-embedding row is added too (feat = cond + temb, head :367-372).
+struct ApplyArgs {
+  const float* y;          // [B][P][C]
+  const float* mean_rstd;  // [B][4][2]
+  const float* gamma;      // [C]
+  const float* beta;       // [C]
+  const float* cond;       // NHWC [B][ch][cw][C]
+  const float* temb;       // [.. ][C], image b uses temb + b*temb_bstride
+  int temb_bstride;
+  int H, W, ch, cw;
+  float ry, rx;            // (ch-1)/(H-1), (cw-1)/(W-1) in fp32 as ATen computes them
+  __half* out_hi;
+  __half* out_lo;
+  float scale;
+  int* status;
+};
+
+template <int C, int COND>
+__global__ void __launch_bounds__(256) gn_apply_split_kernel(const ApplyArgs a) {
+  constexpr int VEC = 8;             // channels per thread
+  constexpr int TPP = C / VEC;       // threads per pixel
+  constexpr int PPB = 256 / TPP;     // pixels per block
+  __shared__ float sa[C], sb[C];
+  const int b = blockIdx.y;
+  const int P = a.H * a.W;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / (C / 4);
+    const float mean = a.mean_rstd[(b * 4 + g) * 2], rstd = a.mean_rstd[(b * 4 + g) * 2 + 1];
+    const float sc = rstd * a.gamma[c];
+    sa[c] = sc;
+    sb[c] = a.beta[c] - sc * mean;
+  }
+  __syncthreads();
+  const int pl = threadIdx.x / TPP, c0 = (threadIdx.x % TPP) * VEC;
+  const int pix = blockIdx.x * PPB + pl;
+  if (pix >= P) return;
+  const size_t off = (static_cast<size_t>(b) * P + pix) * C + c0;
+  float v[VEC];
+  {
+    const float4 u0 = *reinterpret_cast<const float4*>(a.y + off);
+    const float4 u1 = *reinterpret_cast<const float4*>(a.y + off + 4);
+    v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
+    v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) v[j] = fmaxf(fmaf(v[j], sa[c0 + j], sb[c0 + j]), 0.f);
+
+  if constexpr (COND != 0) {
+    const float* te = a.temb + static_cast<size_t>(b) * a.temb_bstride + c0;
+    float cv[VEC];
+    if constexpr (COND == 1) {
+      const float* cp = a.cond + (static_cast<size_t>(b) * P + pix) * C + c0;
+      const float4 u0 = *reinterpret_cast<const float4*>(cp);
+      const float4 u1 = *reinterpret_cast<const float4*>(cp + 4);
+      cv[0] = u0.x; cv[1] = u0.y; cv[2] = u0.z; cv[3] = u0.w;
+      cv[4] = u1.x; cv[5] = u1.y; cv[6] = u1.z; cv[7] = u1.w;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) cv[j] += te[j];
+    } else {
+      // ATen upsample_bilinear2d, align_corners=True: src = scale * dst, lambda1 = frac, lambda0 = 1 - lambda1;
+      // the time embedding is constant over space so interp(cond + temb) == interp(cond) + temb up to rounding;
+      // we follow the reference order: (cond + temb) first, then interpolate.
+      const int oy = pix / a.W, ox = pix % a.W;
+      const float fy = a.ry * oy, fx = a.rx * ox;
+      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+      const int y1 = y0 + (y0 < a.ch - 1 ? 1 : 0), x1 = x0 + (x0 < a.cw - 1 ? 1 : 0);
+      const float ly1 = fy - y0, lx1 = fx - x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      const float* base = a.cond + static_cast<size_t>(b) * a.ch * a.cw * C + c0;
+      const float* p00 = base + (static_cast<size_t>(y0) * a.cw + x0) * C;
+      const float* p01 = base + (static_cast<size_t>(y0) * a.cw + x1) * C;
+      const float* p10 = base + (static_cast<size_t>(y1) * a.cw + x0) * C;
+      const float* p11 = base + (static_cast<size_t>(y1) * a.cw + x1) * C;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 q00 = *reinterpret_cast<const float4*>(p00 + 4 * h);
+        const float4 q01 = *reinterpret_cast<const float4*>(p01 + 4 * h);
+        const float4 q10 = *reinterpret_cast<const float4*>(p10 + 4 * h);
+        const float4 q11 = *reinterpret_cast<const float4*>(p11 + 4 * h);
+        const float t0 = te[4 * h], t1 = te[4 * h + 1], t2 = te[4 * h + 2], t3 = te[4 * h + 3];
+        cv[4 * h + 0] = ly0 * (lx0 * (q00.x + t0) + lx1 * (q01.x + t0)) + ly1 * (lx0 * (q10.x + t0) + lx1 * (q11.x + t0));
+        cv[4 * h + 1] = ly0 * (lx0 * (q00.y + t1) + lx1 * (q01.y + t1)) + ly1 * (lx0 * (q10.y + t1) + lx1 * (q11.y + t1));
+        cv[4 * h + 2] = ly0 * (lx0 * (q00.z + t2) + lx1 * (q01.z + t2)) + ly1 * (lx0 * (q10.z + t2) + lx1 * (q11.z + t2));
+        cv[4 * h + 3] = ly0 * (lx0 * (q00.w + t3) + lx1 * (q01.w + t3)) + ly1 * (lx0 * (q10.w + t3) + lx1 * (q11.w + t3));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = cv[j] + v[j];
+  }
+
+  bool ov = false;
+  __align__(16) __half h[VEC];
+  __align__(16) __half l[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) split_f16(v[j], a.scale, h[j], l[j], ov);
+  *reinterpret_cast<uint4*>(a.out_hi + off) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(a.out_lo + off) = *reinterpret_cast<const uint4*>(l);
+  if (ov) atomicOr(a.status, 1);
+}
+
+// ------------------------------------------------------------------ last GN + ReLU (C = 16) fused with the DDIM update
+// eps = relu(gn(y6));  x <- c_x * x + c_eps * eps   (reference scheduling_ddim.py:285-326 with eta = 0,
+// collapsed).  Also refreshes the fp16 planes of x for the next step's first conv.
+// If eps_out != nullptr, only eps is written (bare denoiser call) and x is left untouched.
+struct FinalArgs {
+  const float* y;          // [B][P][16]
+  const float* mean_rstd;  // [B][4][2]
+  const float* gamma;
+  const float* beta;
+  float* x;                // [B][P][16] fp32 latent (in/out)
+  __half* x_hi;
+  __half* x_lo;
+  float* eps_out;          // optional [B][P][16]
+  float cx, ce, scale;
+  int P;
+  int* status;
+};
+__global__ void __launch_bounds__(256) gn_relu_ddim_kernel(const FinalArgs a) {
+  const int b = blockIdx.y;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;  // float4 index within image
+  if (i >= static_cast<size_t>(a.P) * 4) return;
+  const int g = static_cast<int>(i & 3);  // 16 channels / 4 per float4 = group index
+  const float mean = a.mean_rstd[(b * 4 + g) * 2], rstd = a.mean_rstd[(b * 4 + g) * 2 + 1];
+  const size_t o4 = static_cast<size_t>(b) * a.P * 4 + i;
+  const float4 yv = reinterpret_cast<const float4*>(a.y)[o4];
+  const float4 ga = reinterpret_cast<const float4*>(a.gamma)[g];
+  const float4 be = reinterpret_cast<const float4*>(a.beta)[g];
+  float e[4] = {yv.x, yv.y, yv.z, yv.w};
+  const float gg[4] = {ga.x, ga.y, ga.z, ga.w}, bb[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float sc = rstd * gg[j];
+    e[j] = fmaxf(fmaf(e[j], sc, bb[j] - sc * mean), 0.f);
+  }
+  if (a.eps_out) {
+    reinterpret_cast<float4*>(a.eps_out)[o4] = make_float4(e[0], e[1], e[2], e[3]);
+    return;
+  }
+  const float4 xv = reinterpret_cast<const float4*>(a.x)[o4];
+  float xn[4] = {xv.x, xv.y, xv.z, xv.w};
+  bool ov = false;
+  __align__(8) __half h[4];
+  __align__(8) __half l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    xn[j] = a.cx * xn[j] + a.ce * e[j];
+    split_f16(xn[j], a.scale, h[j], l[j], ov);
+  }
+  reinterpret_cast<float4*>(a.x)[o4] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+  reinterpret_cast<uint2*>(a.x_hi)[o4] = *reinterpret_cast<const uint2*>(h);
+  reinterpret_cast<uint2*>(a.x_lo)[o4] = *reinterpret_cast<const uint2*>(l);
+  if (ov) atomicOr(a.status, 1);
+}
+
+// ------------------------------------------------------------------ fp32 CUDA-core 3x3 conv (validation / DD_FLAG_SIMT_CONV)
+// Same operands and epilogues as the tcgen05 kernel: input fp16 hi/lo planes (x = (hi+lo)/scale), weights fp32
+// [tap][CIN][COUT].  One block = one 8x16 pixel tile x CO_T output channels.
+struct SimtArgs {
+  const __half* in_hi;
+  const __half* in_lo;
+  float in_inv_scale;
+  const float* w;          // [9][CIN][COUT]
+  ConvArgs c;
+};
+
+template <int CIN, int COUT, int EPI>
+__global__ void __launch_bounds__(256) conv3x3_simt_kernel(const SimtArgs a) {
+  constexpr int CO_T = COUT < 64 ? COUT : 64;
+  constexpr int CK = 16;                 // input channels per smem chunk
+  constexpr int CGS = CO_T / 4;          // channel groups of 4
+  constexpr int PGS = 256 / CGS;         // pixel groups
+  constexpr int PXT = TILE_M / PGS;      // pixels per thread (8 or 2)
+  __shared__ float s_in[(TILE_H + 2) * (TILE_W + 2)][CK];
+  __shared__ float s_w[9][CK][CO_T];
+  __shared__ float s_red[4][2];
+  const ConvArgs& p = a.c;
+  const int tile = blockIdx.x;
+  const int co0 = blockIdx.y * CO_T;
+  const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+  const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+  const int cg = threadIdx.x % CGS, pg = threadIdx.x / CGS;
+  float acc[PXT][4];
+#pragma unroll
+  for (int i = 0; i < PXT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (threadIdx.x < 8) (&s_red[0][0])[threadIdx.x] = 0.f;
+
+  for (int k0 = 0; k0 < CIN; k0 += CK) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (TILE_H + 2) * (TILE_W + 2) * CK; i += 256) {
+      const int ci = i % CK, hp = i / CK;
+      const int yy = y0 + hp / (TILE_W + 2) - 1, xx = x0 + hp % (TILE_W + 2) - 1;
+      float v = 0.f;
+      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+        const size_t o = ((static_cast<size_t>(img) * p.H + yy) * p.W + xx) * CIN + k0 + ci;
+        v = (__half2float(a.in_hi[o]) + __half2float(a.in_lo[o])) * a.in_inv_scale;
+      }
+      s_in[hp][ci] = v;
+    }
+    for (int i = threadIdx.x; i < 9 * CK * CO_T; i += 256) {
+      const int co = i % CO_T, ci = (i / CO_T) % CK, tap = i / (CO_T * CK);
+      s_w[tap][ci][co] = a.w[(static_cast<size_t>(tap) * CIN + k0 + ci) * COUT + co0 + co];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap % 3;
+#pragma unroll 4
+      for (int ci = 0; ci < CK; ++ci) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&s_w[tap][ci][cg * 4]);
+#pragma unroll
+        for (int i = 0; i < PXT; ++i) {
+          const int m = pg * PXT + i;
+          const float v = s_in[((m >> 4) + dy) * (TILE_W + 2) + (m & 15) + dx][ci];
+          acc[i][0] = fmaf(v, w4.x, acc[i][0]);
+          acc[i][1] = fmaf(v, w4.y, acc[i][1]);
+          acc[i][2] = fmaf(v, w4.z, acc[i][2]);
+          acc[i][3] = fmaf(v, w4.w, acc[i][3]);
+        }
+      }
+    }
+  }
+  // epilogue
+  float ls[4] = {0.f, 0.f, 0.f, 0.f}, ls2[4] = {0.f, 0.f, 0.f, 0.f};
+  bool ov = false;
+#pragma unroll
+  for (int i = 0; i < PXT; ++i) {
+    const int m = pg * PXT + i;
+    const int y = y0 + (m >> 4), x = x0 + (m & 15);
+    if (y >= p.H || x >= p.W) continue;
+    const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + p.bias[co0 + cg * 4 + j];
+    if constexpr (EPI == EPI_SPLIT) {
+      __align__(8) __half h[4];
+      __align__(8) __half l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_f16(v[j], p.split_scale, h[j], l[j], ov);
+      *reinterpret_cast<uint2*>(p.out_hi + pix * COUT + co0 + cg * 4) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(p.out_lo + pix * COUT + co0 + cg * 4) = *reinterpret_cast<const uint2*>(l);
+    } else {
+      *reinterpret_cast<float4*>(p.y32 + pix * COUT + co0 + cg * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      if constexpr (EPI == EPI_F32_STATS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int g = (co0 + cg * 4 + j) / (COUT / 4);
+          const int gl = (COUT / 4 >= CO_T) ? 0 : (g - co0 / (COUT / 4));
+          ls[gl] += v[j];
+          ls2[gl] = fmaf(v[j], v[j], ls2[gl]);
+        }
+      }
+    }
+  }
+  if constexpr (EPI == EPI_F32_STATS) {
+    constexpr int NG = (COUT / 4 >= CO_T) ? 1 : CO_T / (COUT / 4);  // groups covered by this block
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      atomicAdd(&s_red[g][0], ls[g]);
+      atomicAdd(&s_red[g][1], ls2[g]);
+    }
+    __syncthreads();
+    if (threadIdx.x < NG * 2) {
+      const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+      const int gg = co0 / (COUT / 4) + g;
+      p.stats_partial[(static_cast<size_t>(tile) * 4 + gg) * 2 + which] = s_red[g][which];
+    }
+  }
+  if constexpr (EPI == EPI_SPLIT) {
+    if (ov) atomicOr(p.status, 1);
+  }
+}
+
+// ------------------------------------------------------------------ depth-latent decoder (inv_t), fully fused
+// ConvTranspose2d(16,16,k4,s2,p1)+b -> BN(eval, folded) -> ReLU -> Conv2d(16,1,3,1,1)+b -> z
+// depth = 1 / clamp(sigmoid(z), 1e-6) - 1          (reference src/model/ops/depth_transform.py:20-26,33-35)
+// One block = 8 x 32 output pixels; latent patch and the 10 x 34 x 16 intermediate stay in shared memory.
+struct DecoderArgs {
+  const float* x;      // latent NHWC [B][h][w][16]
+  const float* wt;     // folded ConvT weights [ky][kx][ci][co]
+  const float* bt;     // folded bias [16]
+  const float* wc;     // final conv [tap][ci]
+  float bc;            // final conv bias
+  float* logit;        // optional [B][2h][2w]
+  float* depth;        // [B][2h][2w]
+  int h, w;
+  float eps;
+};
+constexpr int DEC_TH = 8, DEC_TW = 32;
+__global__ void __launch_bounds__(256) decoder_kernel(const DecoderArgs a) {
+  constexpr int LH = DEC_TH / 2 + 2, LW = DEC_TW / 2 + 2;  // latent patch 6 x 18
+  constexpr int MH = DEC_TH + 2, MW = DEC_TW + 2;          // intermediate 10 x 34
+  __shared__ float s_lat[LH * LW][16];
+  __shared__ float s_mid[MH * MW][17];
+  __shared__ float s_wt[16 * 16 * 16];
+  __shared__ float s_wc[9 * 16];
+  __shared__ float s_bt[16];
+  const int b = blockIdx.z;
+  const int Y0 = blockIdx.y * DEC_TH, X0 = blockIdx.x * DEC_TW;
+  const int H = 2 * a.h, W = 2 * a.w;
+  for (int i = threadIdx.x; i < 4096; i += 256) s_wt[i] = a.wt[i];
+  if (threadIdx.x < 144) s_wc[threadIdx.x] = a.wc[threadIdx.x];
+  if (threadIdx.x < 16) s_bt[threadIdx.x] = a.bt[threadIdx.x];
+  const int ly0 = Y0 / 2 - 1, lx0 = X0 / 2 - 1;
+  for (int i = threadIdx.x; i < LH * LW * 4; i += 256) {
+    const int q = i & 3, lp = i >> 2;
+    const int yy = ly0 + lp / LW, xx = lx0 + lp % LW;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w)
+      v = reinterpret_cast<const float4*>(a.x + ((static_cast<size_t>(b) * a.h + yy) * a.w + xx) * 16)[q];
+    s_lat[lp][q * 4 + 0] = v.x;
+    s_lat[lp][q * 4 + 1] = v.y;
+    s_lat[lp][q * 4 + 2] = v.z;
+    s_lat[lp][q * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  // transposed conv: out(Y, X) gathers the 2x2 latent pixels iy = (Y + 1 - ky) / 2 with matching parity
+  for (int i = threadIdx.x; i < MH * MW * 4; i += 256) {
+    const int cq = i & 3, mp = i >> 2;  // 4 output channels per work item
+    const int Y = Y0 - 1 + mp / MW, X = X0 - 1 + mp % MW;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (Y >= 0 && Y < H && X >= 0 && X < W) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = s_bt[cq * 4 + j];
+      const int ky0 = (Y + 1) & 1, kx0 = (X + 1) & 1;
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2) {
+        const int ky = ky0 + 2 * a2;
+        const int iy = (Y + 1 - ky) / 2;  // exact: numerator even
+        if (Y + 1 - ky < 0 || iy >= a.h) continue;
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+          const int kx = kx0 + 2 * b2;
+          const int ix = (X + 1 - kx) / 2;
+          if (X + 1 - kx < 0 || ix >= a.w) continue;
+          const float* lp = s_lat[(iy - ly0) * LW + (ix - lx0)];
+          const float* wp = s_wt + ((ky * 4 + kx) * 16) * 16 + cq * 4;
+#pragma unroll
+          for (int ci = 0; ci < 16; ++ci) {
+            const float v = lp[ci];
+            o[0] = fmaf(v, wp[ci * 16 + 0], o[0]);
+            o[1] = fmaf(v, wp[ci * 16 + 1], o[1]);
+            o[2] = fmaf(v, wp[ci * 16 + 2], o[2]);
+            o[3] = fmaf(v, wp[ci * 16 + 3], o[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_mid[mp][cq * 4 + j] = o[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < DEC_TH * DEC_TW; i += 256) {
+    const int yy = i / DEC_TW, xx = i % DEC_TW;
+    const int Y = Y0 + yy, X = X0 + xx;
+    if (Y >= H || X >= W) continue;
+    float z = a.bc;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float* mp = s_mid[(yy + tap / 3) * MW + xx + tap % 3];
+#pragma unroll
+      for (int ci = 0; ci < 16; ++ci) z = fmaf(mp[ci], s_wc[tap * 16 + ci], z);
+    }
+    const size_t o = (static_cast<size_t>(b) * H + Y) * W + X;
+    if (a.logit) a.logit[o] = z;
+    const float s = 1.0f / (1.0f + expf(-z));
+    a.depth[o] = 1.0f / fmaxf(s, a.eps) - 1.0f;
+  }
+}
+
+}  // namespace dd

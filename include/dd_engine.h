@@ -1,0 +1,143 @@
+/*
+ * dd_engine.h — C ABI of libddengine.so: the B200-native (sm_100a) DiffusionDepth hot path.
+ *
+ * The reference (duanyiqun/DiffusionDepth @ e1ca9d5) has no FFI on this path; these entry points
+ * are what a binding for it would bind.  Each one names the reference interface it replaces:
+ *
+ *   dd_create / dd_destroy        <- construction of `ScheduledCNNRefine` + `CNNDDIMPipiline` +
+ *                                    `DeepDepthTransformWithUpsampling` inside the head ctor
+ *                                    (src/model/head/ddim_depth_estimate_res_swin_addHAHI.py:45-49,
+ *                                     src/model/head/ddim_depth_estimate_res.py:36-40)
+ *   dd_set_weight / dd_finalize_weights
+ *                                 <- `load_state_dict(ckpt['net'])` for the keys under
+ *                                    `depth_head.model.*` and `depth_head.depth_transform.*`
+ *                                    (src/main.py:418-432; key layout SURVEY.md Appendix A)
+ *   dd_set_schedule               <- `DDIMScheduler.set_timesteps` + the per-step scalar algebra of
+ *                                    `DDIMScheduler.step` (src/model/diffusers/schedulers/
+ *                                    scheduling_ddim.py:215-229, 285-326) collapsed to
+ *                                    x_{t-1} = c_x * x_t + c_eps * eps
+ *   dd_denoise_decode             <- `CNNDDIMPipiline.__call__` (head :254-303) = T x
+ *                                    {`ScheduledCNNRefine.forward` (:361-382 / res.py:324-344),
+ *                                    `DDIMScheduler.step`} followed by
+ *                                    `DeepDepthTransformWithUpsampling.inv_t`
+ *                                    (src/model/ops/depth_transform.py:33-35)
+ *   dd_denoiser_forward           <- one bare `ScheduledCNNRefine.forward(noisy, t, cond, ...)` call
+ *                                    (the operator `ddim_loss` invokes, head :207-223)
+ *   dd_decode                     <- `depth_transform.inv_t(latent)` alone (the *Vis heads call it
+ *                                    per step, ..._swin_addHAHI_vis.py)
+ *
+ * Conventions (inherited from the reference): every tensor is fp32, NCHW, contiguous,
+ * resident on the engine's CUDA device; no autograd.  Ownership: the caller (PyTorch's allocator)
+ * owns every buffer including the workspace; the engine borrows raw pointers for the duration of a
+ * call and owns only its pre-packed weights / descriptors / CUDA graph.  Calls are enqueued on the
+ * given stream and return without synchronising.  One handle per (process, device); a handle is not
+ * re-entrant.  Errors: int status (0 = ok), never an exception across the ABI; text via
+ * dd_last_error() (thread-local).  There is NO CPU path: dd_create fails if no sm_100 device is present.
+ */
+#ifndef DD_ENGINE_H_
+#define DD_ENGINE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_ABI_VERSION 1
+
+typedef struct dd_engine* dd_handle;
+
+enum dd_status {
+  DD_OK = 0,
+  DD_ERR_INVALID = 1,     /* bad argument / shape / missing weight */
+  DD_ERR_CUDA = 2,        /* a CUDA runtime or driver call failed */
+  DD_ERR_UNSUPPORTED = 3, /* no sm_100 device, unsupported shape */
+  DD_ERR_RANGE = 4        /* an activation left the fp16 split's range (see DESIGN.md "Numerics") */
+};
+
+enum dd_variant {
+  DD_VARIANT_RES = 0,  /* DDIMDepthEstimate_Res: cond at latent resolution, no upsample_fuse */
+  DD_VARIANT_SWIN = 1  /* DDIMDepthEstimate_Swin_ADDHAHI: cond upsampled (bilinear, align_corners)
+                          to the latent grid, then convA/convB */
+};
+
+enum dd_flags {
+  DD_FLAG_CUDA_GRAPH = 1 << 0, /* capture the T-step loop once and replay it */
+  DD_FLAG_SIMT_CONV = 1 << 1,  /* debug: fp32 CUDA-core convolutions instead of tcgen05 */
+  DD_FLAG_CHECK_RANGE = 1 << 2 /* after the call, sync and report DD_ERR_RANGE if the split overflowed */
+};
+
+typedef struct dd_config {
+  int32_t abi_version;          /* must be DD_ABI_VERSION */
+  int32_t variant;              /* enum dd_variant */
+  int32_t batch;                /* images per call on this device */
+  int32_t latent_h, latent_w;   /* h = ceil(H/2), w = ceil(W/2): shape of depth_transform.t(gt) */
+  int32_t cond_h, cond_w;       /* spatial size of the FPN condition map x (256 channels) */
+  int32_t num_inference_steps;  /* T */
+  int32_t device;               /* CUDA ordinal */
+  int32_t flags;                /* enum dd_flags */
+} dd_config;
+
+/* Fixed by the reference architecture (head ctor): 16 latent channels, 256 condition channels,
+ * GroupNorm(4, C), time_embedding rows = 1280. */
+#define DD_LATENT_C 16
+#define DD_COND_C 256
+#define DD_TIME_ROWS 1280
+
+int dd_abi_version(void);
+const char* dd_last_error(void);
+
+int dd_create(const dd_config* cfg, dd_handle* out);
+int dd_destroy(dd_handle h);
+
+/* Register one parameter/buffer by its reference state_dict key relative to `depth_head.`
+ * (e.g. "model.noise_embedding.0.weight", "depth_transform.conv_inv_transform.1.running_var").
+ * `dev_ptr` is a device fp32 pointer in the reference's own layout/shape; it is read during
+ * dd_finalize_weights only.  Unknown keys are rejected (DD_ERR_INVALID). */
+int dd_set_weight(dd_handle h, const char* name, const float* dev_ptr, const int64_t* shape, int32_t ndim);
+
+/* Pre-pack: fold eval-BatchNorm into the decoder, repack conv weights tap-major, split them into
+ * scaled fp16 hi/lo planes for the 3-pass tensor-core product.  Fails listing any missing key. */
+int dd_finalize_weights(dd_handle h, void* cuda_stream);
+
+/* Per-step timesteps (descending, as DDIMScheduler.set_timesteps produces) and the collapsed DDIM
+ * coefficients; n must equal num_inference_steps. */
+int dd_set_schedule(dd_handle h, const int64_t* timesteps, const double* c_x, const double* c_eps, int32_t n);
+
+size_t dd_workspace_bytes(dd_handle h);
+
+/* cond [B,256,cond_h,cond_w], noise [B,16,h,w] -> latent_out [B,16,h,w] (nullable),
+ * logit_out [B,1,2h,2w] (nullable; the decoder's pre-sigmoid z), depth_out [B,1,2h,2w]. */
+int dd_denoise_decode(dd_handle h, const float* cond, const float* noise, float* latent_out, float* logit_out,
+                      float* depth_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* eps = ScheduledCNNRefine(noisy, t, cond): noisy [B,16,h,w], t[b] int64 host array (one per image),
+ * eps_out [B,16,h,w]. */
+int dd_denoiser_forward(dd_handle h, const float* cond, const float* noisy, const int64_t* t_host, float* eps_out,
+                        void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* depth = inv_t(latent): latent [B,16,h,w] -> logit_out (nullable), depth_out [B,1,2h,2w]. */
+int dd_decode(dd_handle h, const float* latent, float* logit_out, float* depth_out, void* workspace,
+              size_t workspace_bytes, void* cuda_stream);
+
+/* Number of kernel launches the last dd_denoise_decode enqueued (graph nodes count individually). */
+int64_t dd_last_launch_count(dd_handle h);
+
+/* Standalone layer entry used by the parity tests and the roofline bench: one 3x3/s1/p1 convolution
+ * + bias on the engine's tensor-core (or SIMT, per flags) path.
+ * x [B,Cin,H,W], w [Cout,Cin,3,3], b [Cout] -> y [B,Cout,H,W]; all device fp32 NCHW. */
+int dd_conv3x3(dd_handle h, const float* x, const float* w, const float* b, float* y, int32_t batch, int32_t cin,
+               int32_t cout, int32_t height, int32_t width, void* workspace, size_t workspace_bytes,
+               void* cuda_stream);
+size_t dd_conv3x3_workspace_bytes(int32_t batch, int32_t cin, int32_t cout, int32_t height, int32_t width);
+
+/* Time the dominant kernel (convA-shaped 256->256 3x3 on the engine's latent grid) `iters` times with
+ * CUDA events on `cuda_stream`; returns average milliseconds per launch in *ms_out. */
+int dd_bench_conv(dd_handle h, int32_t cin, int32_t cout, int32_t iters, float* ms_out, void* workspace,
+                  size_t workspace_bytes, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DD_ENGINE_H_ */
