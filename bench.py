@@ -1,0 +1,231 @@
+#!/usr/bin/env python
+"""bench.py — depth maps/sec @ KITTI 352x1216, Swin-L, 20 DDIM steps (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference ...                   the reference's CPU path (oracle port), rank 0 only
+
+A "step" is one forward of the per-GPU batch (BASELINE config 3: 4 images, 352x1216, Swin-L, T=20) through the
+plugin (`Diffusion_DCbase_Model.forward`): backbone + neck/FPN (torch, fp32, TF32 off) + the CUDA engine's
+T-step DDIM loop + decoder; for N > 1 the batch shards by rank (weak scaling: 4 images/GPU = BASELINE config 4
+at N = 8) and each step ends with the single all-gather of the depth maps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "depth maps/sec @ KITTI 352x1216, Swin-L, 20 DDIM steps"
+WORKLOADS = {  # name -> (family, T, per-GPU batch, H, W, GFLOP per map: BASELINE.md work table)
+    "C3": ("swinl", 20, 4, 352, 1216, 7258.7),
+    "C2": ("res50", 20, 8, 228, 304, 270.5),
+    "C5": ("swinl", 50, 8, 480, 640, 12083.0),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+
+
+def cpu_reference_maps_per_s(workload, steps=1, warmup=0):
+    """The reference's CPU path (oracle port of its forward: same torch CPU ops, all host threads) on a bounded
+    sample of the workload: ONE image of the configured size per step."""
+    from oracle import configs, restate
+    import dd_helpers  # noqa: F401  (tests/ helper: mirror construction under the golden seed)
+    family, T, _, H, W, _ = WORKLOADS[workload]
+    m = dd_helpers.build_mirror(family, T)
+    sd = m.state_dict()
+    sample = restate.synthetic_sample(1, H, W, configs.SEED_INPUTS)
+    noise = restate.synthetic_noise(1, H, W, configs.SEED_NOISE)
+    bb = configs.FAMILIES[family]["backbone_name"]
+    for _ in range(warmup):
+        restate.forward(sd, sample, bb, T, noise)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        restate.forward(sd, sample, bb, T, noise)
+    dt = (time.perf_counter() - t0) / steps
+    return 1.0 / dt, dt, f"1 image {H}x{W}, T={T}, full forward (backbone+neck+FPN+loop+decoder), fp32, {torch.get_num_threads()} threads"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    family, T, B, H, W, gflop_map = WORKLOADS[args.workload]
+    cfg = {"workload": f"{args.workload}: {family} backbone, T={T} DDIM steps, {B}x{H}x{W} per GPU (synthetic)",
+           "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}",
+           "l2": "per-step working set ~1.3 GB of activations streamed per conv >> 126 MB L2 (no cross-step reuse)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        torch.set_num_threads(os.cpu_count() or 1)
+        v, dt, what = cpu_reference_maps_per_s(args.workload, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "maps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": "maps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": what},
+            "e2e": {"value": v, "unit": "maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import diffusiondepth_b200 as dd
+    from diffusiondepth_b200 import shard
+    from oracle import configs, restate
+    import dd_helpers
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a B200; there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    model = dd_helpers.build_mirror(family, T).to(dev)
+    model.depth_head.use_cuda_graph = not args.no_graph
+    model.depth_head.check_range = False
+    first, _ = shard.shard_range(B * world, rank, world)
+    host = restate.synthetic_sample(B, H, W, configs.SEED_INPUTS, first=first)
+    host["noise"] = restate.synthetic_noise(B, H, W, configs.SEED_NOISE, first=first)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+
+    def step_resident():
+        with torch.no_grad():
+            out = model(resident)
+        pred = out["pred"]
+        return shard.gather_depth(pred, B * world) if world > 1 else pred
+
+    def step_e2e():
+        with torch.no_grad():
+            out = model({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+        pred = shard.gather_depth(out["pred"], B * world) if world > 1 else out["pred"]
+        return pred[first:first + B].to("cpu", non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    eng = next(iter(model.depth_head._engines.values()))
+    eng.poll_status()  # the split must not have overflowed on this workload
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.last_launch_count * args.steps
+    value = B * world * args.steps / (ms / 1e3)
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = B * world * args.steps / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = B * H * W * 4
+
+    # roofline of the dominant kernel: the 256->256 3x3 conv (convA/convB = 79 % of the loop's FLOPs)
+    pk = peaks()
+    roof = None
+    if rank == 0:
+        cin, cout = (256, 256) if family == "swinl" else (256, 64)
+        iters = 20
+        kms = eng.bench_conv(cin, cout, iters)
+        P = B * ((H + 1) // 2) * ((W + 1) // 2)
+        flops = 2.0 * P * cout * 9 * cin  # algorithmic (one fp32-grade product-sum per MAC), not the 3x issued
+        ach = flops / (kms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": f"conv3x3_umma_kernel<{cin},{cout}>", "achieved": ach, "peak": pk["tf_burst"],
+                "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "issued_frac": 3 * ach / pk["tf_burst"],
+                "ms_per_launch": kms, "traffic": None, "peak_source": pk["source"] + ", bf16 burst",
+                "note": "achieved = algorithmic FLOPs; the 3-pass fp16 split issues 3x that on the tensor pipe, so 1/3 is the ceiling"}
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        v, dt, what = cpu_reference_maps_per_s(args.workload, steps=1, warmup=0)
+        cpu = {"value": v, "unit": "maps/s", "cores": torch.get_num_threads(), "kind": "port", "sample": what,
+               "seconds": dt}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "maps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (3-pass fp16 split on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "config": cfg, "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "roofline": roof, "cpu_baseline": cpu,
+            "algorithmic_tflops": value * gflop_map / 1e3, "frac_of_bf16_sustained": value * gflop_map / 1e3 / pk["tf_sustained"]}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -750,6 +750,13 @@ int dd_decode(dd_handle h, const float* latent, float* logit_out, float* depth_o
 
 int64_t dd_last_launch_count(dd_handle h) { return h ? h->launches : 0; }
 
+int dd_poll_status(dd_handle h, void* cuda_stream) {
+  if (!h) return fail(DD_ERR_INVALID, "null handle");
+  if (!h->status) return DD_OK;  // nothing has run yet
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  return poll_status(h, static_cast<cudaStream_t>(cuda_stream));
+}
+
 // ---------------------------------------------------------------- standalone conv (tests / roofline)
 size_t dd_conv3x3_workspace_bytes(int32_t batch, int32_t cin, int32_t cout, int32_t height, int32_t width) {
   const size_t BP = static_cast<size_t>(batch) * height * width;

@@ -172,6 +172,10 @@ class DenoiseEngine:
                                            ws.numel() - 1024, C.c_void_p(self._stream())))
         return float(ms.value)
 
+    def poll_status(self) -> None:
+        """Synchronise the current stream; raises EngineError(DD_ERR_RANGE) if the fp16 split overflowed."""
+        _cabi.check(self.lib.dd_poll_status(self._h, C.c_void_p(self._stream())))
+
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.dd_last_launch_count(self._h))

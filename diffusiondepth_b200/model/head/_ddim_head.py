@@ -1,0 +1,186 @@
+"""Shared machinery of the DDIM depth heads: parameter containers with the reference's key layout and the
+bridge to the CUDA engine.
+
+Reference call chain being replaced (src/model/head/ddim_depth_estimate_res_swin_addHAHI.py):
+  forward :87-185  ->  pipeline(...) :130-144  = CNNDDIMPipiline.__call__ :254-303 (T x {denoiser :361-382,
+  DDIMScheduler.step})  ->  depth_transform.inv_t :146.
+Here: FPN / neck stay torch ops (step-invariant, once per image); loop + decoder = one C-ABI call."""
+import weakref
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..._cabi import EngineError
+from ...engine import DECODER_KEYS, DENOISER_KEYS, FUSE_KEYS, DenoiseEngine
+from .._blocks import ConvModule, exact_fp32
+from ..diffusers.schedulers.scheduling_ddim import DDIMScheduler
+from ..ops import depth_transform as _codec  # noqa: F401  (registers the codec classes)
+from ..registry import DEPTH_TRANSFORM
+
+FPN_DIM = 256
+
+
+def _gn_conv_stack(cin, mid, cout):
+    """conv3x3 -> GN(4) -> ReLU -> conv3x3 -> GN(4) -> ReLU; indices 0,1,3,4 carry parameters."""
+    return nn.Sequential(nn.Conv2d(cin, mid, 3, 1, 1), nn.GroupNorm(4, mid), nn.ReLU(True),
+                         nn.Conv2d(mid, cout, 3, 1, 1), nn.GroupNorm(4, cout), nn.ReLU(True))
+
+
+class UpSample_add(nn.Module):
+    """Parameters of the Swin heads' fusion block: convA / convB = bare 3x3 conv + bias (head :321-333)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.convA = ConvModule(cin, cout, 3, padding=1, norm=False, act=False)
+        self.convB = ConvModule(cout, cout, 3, padding=1, norm=False, act=False)
+
+
+class ScheduledCNNRefine(nn.Module):
+    """The denoiser's parameters (head :336-359 / res.py:301-322).  It has no torch forward: the operator
+    `model(noisy, t, cond, None, None, None) -> eps` is served by the engine (`DenoiseEngine.denoiser_forward`)."""
+
+    def __init__(self, channels_in, channels_noise, with_fuse):
+        super().__init__()
+        self.noise_embedding = _gn_conv_stack(channels_noise, 64, channels_in)
+        if with_fuse:
+            self.upsample_fuse = UpSample_add(channels_in, channels_in)
+        self.time_embedding = nn.Embedding(1280, channels_in)
+        self.pred = _gn_conv_stack(channels_in, 64, channels_noise)
+        self.__dict__['_bridge'] = None  # weakref to the owning head, set by it
+
+    def forward(self, noisy_image, t, feat, *unused):
+        head = self._bridge() if self._bridge is not None else None
+        if head is None:
+            raise EngineError("ScheduledCNNRefine is not attached to a DDIM head / CUDA engine")
+        return head.denoiser(noisy_image, t, feat)
+
+
+def _fpn_lateral(cin):
+    return nn.Sequential(nn.Conv2d(cin, FPN_DIM, 3, 1, 1, bias=False), nn.BatchNorm2d(FPN_DIM), nn.ReLU(True))
+
+
+def _fpn_up():
+    return nn.Sequential(nn.ConvTranspose2d(FPN_DIM, FPN_DIM, 2, 2, bias=False), nn.BatchNorm2d(FPN_DIM), nn.ReLU(True))
+
+
+class DDIMHeadBase(nn.Module):
+    """Common ctor surface: HEADS.build(dict(type=..., in_channels, inference_steps, num_train_timesteps,
+    depth_feature_dim=16, loss_cfgs, init_cfg=args)) as in reference diffusion_dcbase_model.py:77-91."""
+
+    variant = "res"          # engine variant
+    fpn_in_channels = (64, 128, 256, 512)
+    return_intermediates = False  # *Vis heads: also decode every intermediate latent -> 'pred_inter'
+
+    def __init__(self, in_channels=None, up_scale_factor=1, inference_steps=20, num_train_timesteps=1000,
+                 return_indices=None, depth_transform_cfg=None, detach_fp=False, depth_embed_dim=16,
+                 depth_feature_dim=16, loss_cfgs=(), init_cfg=None, **unused):
+        super().__init__()
+        self.init_cfg, self.detach_fp, self.loss_cfgs = init_cfg, detach_fp, list(loss_cfgs)
+        self.return_indices = return_indices
+        self.depth_embed_dim = depth_embed_dim
+        cfg = depth_transform_cfg or dict(type="DeepDepthTransformWithUpsampling", hidden=16, eps=1e-6)
+        self.depth_transform = DEPTH_TRANSFORM.build(cfg)
+        self.model = ScheduledCNNRefine(FPN_DIM, depth_feature_dim, with_fuse=self.variant == "swin")
+        self.model.__dict__['_bridge'] = weakref.ref(self)  # plain attribute: must not register as a submodule
+        self.diffusion_inference_steps = inference_steps
+        self.scheduler = DDIMScheduler(num_train_timesteps=num_train_timesteps, clip_sample=False)
+        self.conv_lateral = nn.ModuleList(_fpn_lateral(c) for c in self.fpn_in_channels)
+        self.conv_up = nn.ModuleList(_fpn_up() for _ in self.fpn_in_channels[1:])
+        # engine state (not parameters)
+        self.eval_ddim_loss = False       # reference computes it in eval too; it is RNG noise there
+        self.use_cuda_graph = True
+        self.check_range = True
+        self.capture_logits = False      # tests: also keep the decoder's pre-sigmoid z of the last forward
+        self.noise_generator: Optional[torch.Generator] = None
+        self._engines: Dict[Tuple, DenoiseEngine] = {}
+        self._packed_sig = {}
+
+    # ------------------------------------------------------------------------------------------ engine bridge
+    def _engine_tensors(self):
+        sd = {}
+        for k in DENOISER_KEYS + DECODER_KEYS + (FUSE_KEYS if self.variant == "swin" else ()):
+            mod, _, leaf = k.rpartition(".")
+            obj = self.get_submodule(mod)
+            sd[k] = getattr(obj, leaf)
+        return sd
+
+    def _engine(self, batch, latent_hw, cond_hw, device) -> DenoiseEngine:
+        key = (batch, tuple(latent_hw), tuple(cond_hw), str(device), self.diffusion_inference_steps,
+               self.use_cuda_graph)
+        eng = self._engines.get(key)
+        tensors = self._engine_tensors()
+        sig = tuple((t.data_ptr(), t._version) for t in tensors.values())
+        if eng is None:
+            eng = DenoiseEngine(self.variant, batch, latent_hw, cond_hw, self.diffusion_inference_steps, device,
+                                cuda_graph=self.use_cuda_graph, check_range=False)
+            ts, cx, ce = self.scheduler.fused_coefficients(self.diffusion_inference_steps)
+            eng.set_schedule(ts, cx, ce)
+            self._engines[key] = eng
+            self._packed_sig.pop(key, None)
+        if self._packed_sig.get(key) != sig:  # first use, or parameters changed (load_state_dict, .to(), ...)
+            eng.load_weights(tensors)
+            self._packed_sig[key] = sig
+        return eng
+
+    def denoiser(self, noisy, t, cond):
+        """`self.model(noisy, t, cond, None, None, None)` of the reference, on the engine."""
+        B = noisy.shape[0]
+        eng = self._engine(B, noisy.shape[-2:], cond.shape[-2:], noisy.device)
+        tl = t.reshape(-1).tolist() if torch.is_tensor(t) else t
+        return eng.denoiser_forward(cond.contiguous().float(), noisy.contiguous().float(), tl)
+
+    # ------------------------------------------------------------------------------------------ condition path
+    def _condition(self, fp):
+        """Top-down FPN that builds the 256-channel condition map x (head :112-122 / res.py:108-118)."""
+        x = None
+        for i in reversed(range(len(fp))):
+            lat = self.conv_lateral[i](fp[i])
+            if x is not None:
+                lat = lat + F.adaptive_avg_pool2d(self.conv_up[i](x), lat.shape[-2:])
+            x = lat
+        return x
+
+    def _neck(self, fp):
+        return fp
+
+    def _draw_noise(self, shape, device, dtype, override):
+        if override is not None:
+            return override.to(device=device, dtype=dtype).contiguous()
+        g = self.noise_generator
+        if g is not None and g.device.type != torch.device(device).type:
+            return torch.randn(shape, generator=g, dtype=dtype).to(device)
+        return torch.randn(shape, generator=g, device=device, dtype=dtype)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, fp, depth_map, depth_mask, gt_depth_map=None, return_loss=False, noise=None, **kwargs):
+        if self.detach_fp is not False and self.detach_fp is not None:
+            idx = self.detach_fp if isinstance(self.detach_fp, (list, tuple, range)) else range(len(fp))
+            fp = [f.detach() if i in idx else f for i, f in enumerate(fp)]
+        with torch.no_grad(), exact_fp32():
+            gt_map_t = self.depth_transform.t(gt_depth_map)
+            cond = self._condition(self._neck(fp)).contiguous()
+        B = cond.shape[0]
+        latent_hw = tuple(gt_map_t.shape[-2:])
+        x_T = self._draw_noise((B, *gt_map_t.shape[-3:]), cond.device, cond.dtype, noise)
+        eng = self._engine(B, latent_hw, tuple(cond.shape[-2:]), cond.device)
+        refined_depth, refined_depth_t, logits = eng.denoise_decode(cond, x_T, want_latent=True,
+                                                                    want_logits=self.capture_logits)
+        self.last_latent, self.last_logits, self.last_cond = refined_depth_t, logits, cond
+        if self.check_range:
+            eng.poll_status()  # syncs; raises if an activation left the fp16 split range (DESIGN.md "Numerics")
+        ddim_loss = self._ddim_loss(cond, refined_depth_t) if (self.eval_ddim_loss or self.training) \
+            else refined_depth.new_zeros(())
+        return {'pred': refined_depth, 'pred_init': gt_map_t, 'blur_depth_t': gt_map_t, 'ddim_loss': ddim_loss,
+                'gt_map_t': gt_map_t, 'pred_uncertainty': None, 'pred_inter': None, 'weight_map': None,
+                'guidance': None, 'offset': None, 'aff': None, 'gamma': None, 'confidence': None}
+
+    def _ddim_loss(self, cond, latent):
+        """Reference head :207-223 — one extra denoiser call on a re-noised latent; RNG-dependent."""
+        noise = torch.randn(latent.shape).to(latent.device)
+        t = torch.randint(0, self.scheduler.num_train_timesteps, (latent.shape[0],), device=latent.device).long()
+        noisy = self.scheduler.add_noise(latent, noise, t)
+        return F.mse_loss(self.model(noisy, t, cond, None, None, None), noise)
+
+    ddim_loss = _ddim_loss

@@ -1,0 +1,52 @@
+"""Batch sharding across the GPUs of one box: every op on the path is per-sample, so the only
+exchange is ONE all-gather of the final depth maps.  One process per GPU (torchrun), NCCL over NVLink;
+the same code runs under gloo on CPU for the host-logic tests.  New relative to the reference, whose test
+path is single-process nn.DataParallel at batch 1 (reference src/main.py:434)."""
+from typing import Callable, Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, near-equal shards: (first_index, count) of `rank`; earlier ranks take the remainder."""
+    if not (0 <= rank < world) or global_batch < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(global_batch, world)
+    count = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, count
+
+
+def slice_sample(sample: Dict[str, torch.Tensor], first: int, count: int) -> Dict[str, torch.Tensor]:
+    """Per-rank view of a full-batch sample dict (keys of reference src/data/kittidc.py:273 + optional 'noise')."""
+    return {k: (v[first:first + count] if torch.is_tensor(v) and v.dim() > 0 else v) for k, v in sample.items()}
+
+
+def gather_depth(pred_local: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
+    """The single collective on the path: all ranks end with pred [global_batch,1,H,W].
+    Equal shards -> one `all_gather_into_tensor`; ragged shards pad to the largest shard first."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    counts = [shard_range(global_batch, r, world)[1] for r in range(world)]
+    cmax = max(counts)
+    tail = tuple(pred_local.shape[1:])
+    if pred_local.shape[0] != counts[rank]:
+        raise ValueError(f"rank {rank} holds {pred_local.shape[0]} maps, expected {counts[rank]}")
+    send = pred_local.contiguous()
+    if counts[rank] < cmax:
+        send = torch.cat([send, send.new_zeros((cmax - counts[rank],) + tail)])
+    out = send.new_empty((world * cmax,) + tail)
+    dist.all_gather_into_tensor(out, send, group=group)
+    if all(c == cmax for c in counts):
+        return out
+    return torch.cat([out[r * cmax:r * cmax + c] for r, c in enumerate(counts)])
+
+
+def run_sharded(model: Callable[[Dict[str, torch.Tensor]], Dict[str, torch.Tensor]], sample: Dict[str, torch.Tensor],
+                global_batch: int, group=None) -> torch.Tensor:
+    """Each rank runs `model` on its slice of the full-batch `sample`, then one all-gather of 'pred'."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    first, count = shard_range(global_batch, rank, world)
+    out = model(slice_sample(sample, first, count))
+    return gather_depth(out["pred"], global_batch, group)

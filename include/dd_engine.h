@@ -121,6 +121,11 @@ int dd_denoiser_forward(dd_handle h, const float* cond, const float* noisy, cons
 int dd_decode(dd_handle h, const float* latent, float* logit_out, float* depth_out, void* workspace,
               size_t workspace_bytes, void* cuda_stream);
 
+/* Synchronise `cuda_stream` and report DD_ERR_RANGE if any activation left the fp16 split's range since the
+ * last hot-path call started (DD_OK otherwise).  The hot-path calls themselves never synchronise unless
+ * DD_FLAG_CHECK_RANGE is set. */
+int dd_poll_status(dd_handle h, void* cuda_stream);
+
 /* Number of kernel launches the last dd_denoise_decode enqueued (graph nodes count individually). */
 int64_t dd_last_launch_count(dd_handle h);
 

@@ -1,0 +1,248 @@
+"""GPU parity tests proper (-m gpu): the CUDA path through the C ABI against the oracle restatement on the
+same seeded inputs, against golden vectors from the real reference, and size-independent properties at
+BASELINE.json's full sizes.  Tolerance: 1e-3 on the decoder logit z (== relative depth error)."""
+import pytest
+import torch
+
+import diffusiondepth_b200 as dd
+from oracle import configs, restate
+import dd_helpers as helpers
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+TOL = 1e-3
+SHAPES = [(16, 64), (64, 256), (256, 256), (256, 64), (64, 16)]
+
+
+def _swin_head(steps, seed=7):
+    from diffusiondepth_b200.model.registry import HEADS
+    torch.manual_seed(seed)
+    return HEADS.build(dict(type="DDIMDepthEstimate_Swin_ADDHAHI", in_channels=[64, 128, 256, 512],
+                            inference_steps=steps, num_train_timesteps=1000, depth_feature_dim=16, loss_cfgs=[],
+                            init_cfg=None)).eval()
+
+
+def _res_head(steps, seed=7):
+    from diffusiondepth_b200.model.registry import HEADS
+    torch.manual_seed(seed)
+    return HEADS.build(dict(type="DDIMDepthEstimate_Res", in_channels=[64, 128, 256, 512], inference_steps=steps,
+                            num_train_timesteps=1000, depth_feature_dim=16, loss_cfgs=[], init_cfg=None)).eval()
+
+
+def _head_sd(head):
+    return {"depth_head." + k: v.detach().cpu() for k, v in head.state_dict().items()}
+
+
+# ------------------------------------------------------------------------------------------------ single layers
+@pytest.mark.parametrize("simt", [False, True])
+@pytest.mark.parametrize("cin,cout", SHAPES)
+def test_conv3x3_all_hot_path_shapes(cin, cout, simt):
+    """3-pass fp16 split on tcgen05 (and the fp32 CUDA-core check path) vs an fp64 reference; ragged tiles,
+    a single tile, sub-tile images."""
+    eng = dd.DenoiseEngine("swin", 1, (8, 16), (4, 8), 2, DEV, cuda_graph=False, simt_conv=simt)
+    for (B, H, W) in [(2, 24, 40), (1, 8, 16), (1, 13, 21), (1, 5, 9), (2, 57, 76)]:
+        g = torch.Generator().manual_seed(cin * 1000 + cout + H)
+        x = torch.randn(B, cin, H, W, generator=g).to(DEV) * 3
+        w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).to(DEV)
+        b = torch.randn(cout, generator=g).to(DEV)
+        y = eng.conv3x3(x, w, b)
+        ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1)
+        err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 3e-5, (cin, cout, B, H, W, err)
+    eng.close()
+
+
+def test_conv_linearity_and_zero():
+    eng = dd.DenoiseEngine("swin", 1, (8, 16), (4, 8), 2, DEV, cuda_graph=False)
+    g = torch.Generator().manual_seed(1)
+    x1, x2 = (torch.randn(1, 256, 16, 32, generator=g).to(DEV) for _ in range(2))
+    w = (torch.randn(256, 256, 3, 3, generator=g) * 0.02).to(DEV)
+    zero = torch.zeros(256, device=DEV)
+    y1, y2, y12 = eng.conv3x3(x1, w, zero), eng.conv3x3(x2, w, zero), eng.conv3x3(x1 + x2, w, zero)
+    assert (y12 - y1 - y2).abs().max().item() < 2e-5 * y12.abs().max().item()
+    assert eng.conv3x3(torch.zeros_like(x1), w, zero).abs().max().item() == 0.0
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ operators
+@pytest.mark.parametrize("variant,hw", [("res", (19, 27)), ("swin", (18, 26)), ("swin", (8, 16))])
+def test_denoiser_operator_vs_oracle(variant, hw):
+    """eps = ScheduledCNNRefine(noisy, t, cond) with per-image t — vs the fp64 restatement."""
+    head = (_res_head if variant == "res" else _swin_head)(5).to(DEV)
+    sd = _head_sd(head)
+    B, (h, w) = 2, hw
+    chw = (h, w) if variant == "res" else ((h + 1) // 2, (w + 1) // 2)
+    g = torch.Generator().manual_seed(3)
+    noisy = torch.randn(B, 16, h, w, generator=g) * 4
+    cond = torch.randn(B, 256, *chw, generator=g)
+    t = torch.tensor([950, 40])
+    eps = head.model(noisy.to(DEV), t.to(DEV), cond.to(DEV), None, None, None)
+    ref = restate.denoiser(sd, noisy.double(), t, cond.double(), variant)
+    assert eps.shape == ref.shape and (eps >= 0).all()
+    assert (eps.double().cpu() - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_decoder_vs_oracle():
+    head = _res_head(5).to(DEV)
+    sd = _head_sd(head)
+    g = torch.Generator().manual_seed(4)
+    for (h, w) in [(19, 27), (8, 16), (33, 5)]:
+        lat = torch.randn(2, 16, h, w, generator=g) * 20
+        eng = head._engine(2, (h, w), (h, w), DEV)
+        depth, logits = eng.decode(lat.to(DEV), want_logits=True)
+        z = restate.decode_logits(sd, lat.double())
+        assert (logits.double().cpu() - z).abs().max().item() < 1e-4 * max(1.0, z.abs().max().item())
+        d32 = restate.decode(sd, lat)
+        pm = restate.parity_metrics(logits.cpu(), z.float(), depth.cpu(), d32)
+        assert pm["max_rel_depth_wellcond"] < TOL
+        assert (depth.cpu()[z.float() < -14.5] == 999999.0).all()  # clamp(1e-6) branch of inv_t
+
+
+@pytest.mark.parametrize("variant,hw,T", [("res", (19, 27), 5), ("swin", (18, 26), 5), ("swin", (24, 40), 20)])
+def test_loop_and_decode_vs_oracle(variant, hw, T):
+    """T-step DDIM loop + decoder through dd_denoise_decode vs the fp64 restatement; CUDA-graph replay and the
+    fp32 CUDA-core conv path must agree with it too."""
+    head = (_res_head if variant == "res" else _swin_head)(T).to(DEV)
+    sd = _head_sd(head)
+    B, (h, w) = 2, hw
+    chw = (h, w) if variant == "res" else ((h + 1) // 2, (w + 1) // 2)
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(B, 16, h, w, generator=g)
+    cond = torch.randn(B, 256, *chw, generator=g).abs()
+    lat_ref = restate.ddim_loop(sd, cond.double(), noise.double(), T, variant)
+    z_ref = restate.decode_logits(sd, lat_ref)
+    outs = {}
+    for name, kw in (("graph", dict(cuda_graph=True)), ("eager", dict(cuda_graph=False)),
+                     ("simt", dict(cuda_graph=False, simt_conv=True))):
+        eng = dd.DenoiseEngine(variant, B, (h, w), chw, T, DEV, check_range=True, **kw)
+        eng.load_weights(head._engine_tensors())
+        eng.set_schedule(*head.scheduler.fused_coefficients(T))
+        depth, lat, z = eng.denoise_decode(cond.to(DEV), noise.to(DEV), want_latent=True, want_logits=True)
+        depth2, _, z2 = eng.denoise_decode(cond.to(DEV), noise.to(DEV), want_latent=True, want_logits=True)
+        assert torch.equal(z, z2) and torch.equal(depth, depth2), "run-to-run determinism"
+        outs[name] = z
+        scale = max(1.0, lat_ref.abs().max().item())
+        assert (lat.double().cpu() - lat_ref).abs().max().item() < 2e-4 * scale, name
+        assert (z.double().cpu() - z_ref).abs().max().item() < TOL, name
+        assert eng.last_launch_count == 3 + T * (14 if variant == "swin" else 12) + 2
+        eng.close()
+    assert torch.equal(outs["graph"], outs["eager"])
+
+
+# ------------------------------------------------------------------------------------------------ whole plugin
+def _run_plugin(case, batch=None):
+    g = helpers.load_golden(case)
+    m = helpers.build_mirror(g["family"], g["T"]).to(DEV)
+    ck = helpers.weight_checksum({k: v.cpu() for k, v in m.state_dict().items()})
+    assert abs(ck - float(g["z"]["weight_checksum"])) <= 1e-5 * ck, "regenerated weights differ from the golden's"
+    B = batch or g["B"]
+    sample = restate.synthetic_sample(B, g["H"], g["W"], configs.SEED_INPUTS)
+    sample["noise"] = restate.synthetic_noise(B, g["H"], g["W"], configs.SEED_NOISE)
+    sample = {k: v.to(DEV) for k, v in sample.items()}
+    m.depth_head.capture_logits = True
+    with torch.no_grad():
+        out = m(sample)
+    return g, m, out
+
+
+@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_swinl_small", "g_res50_c2", "g_swinl_c3",
+                                  "g_swinl_c5"])
+def test_plugin_forward_matches_reference_golden(case):
+    """`Diffusion_DCbase_Model.forward(sample)` on the GPU vs the real reference's own forward (golden)."""
+    g, m, out = _run_plugin(case)
+    z = m.depth_head.last_logits.cpu()
+    z_ref = torch.from_numpy(g["z"]["logits"])
+    dz = (helpers.golden_view(g, "logits", z) - z_ref).abs()
+    assert dz.max().item() < TOL, f"{case}: max|dz| {dz.max().item():.3e}"
+    pm = restate.parity_metrics(helpers.golden_view(g, "logits", z), z_ref, helpers.golden_view(g, "pred", out["pred"].cpu()),
+                                torch.from_numpy(g["z"]["pred"]))
+    assert pm["max_rel_depth_wellcond"] < TOL
+    lat = helpers.golden_view(g, "latent", m.depth_head.last_latent.cpu())
+    assert (lat - torch.from_numpy(g["z"]["latent"])).abs().max().item() < 5e-4 * float(g["z"]["latent_absmax"])
+    cond = helpers.golden_view(g, "cond", m.depth_head.last_cond.cpu())
+    assert (cond - torch.from_numpy(g["z"]["cond"])).abs().max().item() < 1e-4 * float(g["z"]["cond_absmax"])
+    assert sorted(out.keys()) == sorted(str(k) for k in g["z"]["output_keys"])
+    assert out["pred"].shape == (g["B"], 1, g["H"], g["W"]) and out["pred_init"].shape[1] == 16
+    for k in ("pred_uncertainty", "pred_inter", "weight_map", "guidance", "offset", "aff", "gamma", "confidence"):
+        assert out[k] is None
+
+
+def test_full_size_c3_batch_properties():
+    """BASELINE config 3 (Swin-L, T=20, 4 x 352 x 1216): image 0 of the batch equals the batch-1 golden, images are
+    independent of their batch neighbours, and the run is deterministic."""
+    g, m, out = _run_plugin("g_swinl_c3", batch=4)
+    z4 = m.depth_head.last_logits.clone()
+    z_ref = torch.from_numpy(g["z"]["logits"])
+    assert (helpers.golden_view(g, "logits", z4[:1].cpu()) - z_ref).abs().max().item() < TOL
+    sample = restate.synthetic_sample(1, g["H"], g["W"], configs.SEED_INPUTS, first=2)
+    sample["noise"] = restate.synthetic_noise(1, g["H"], g["W"], configs.SEED_NOISE, first=2)
+    with torch.no_grad():
+        m({k: v.to(DEV) for k, v in sample.items()})
+    z1 = m.depth_head.last_logits
+    assert (z1[0] - z4[2]).abs().max().item() < 2e-4  # same image alone vs inside a batch of 4
+    _, m2, _ = _run_plugin("g_swinl_c3", batch=4)
+    assert torch.equal(m2.depth_head.last_logits, z4)
+    frac_clamped = (out["pred"] >= 999998.0).float().mean().item()
+    assert abs(frac_clamped - float(g["z"]["frac_clamped"])) < 0.05  # random-init outputs saturate
+
+
+def test_vis_head_and_ddim_loss_key():
+    from diffusiondepth_b200.model.registry import HEADS
+    torch.manual_seed(7)
+    vis = HEADS.build(dict(type="DDIMDepthEstimate_ResVis", in_channels=[64, 128, 256, 512], inference_steps=5,
+                           num_train_timesteps=1000, depth_feature_dim=16, loss_cfgs=[], init_cfg=None)).eval().to(DEV)
+    base = _res_head(5).to(DEV)
+    base.load_state_dict(vis.state_dict())
+    g = torch.Generator().manual_seed(9)
+    fp = [torch.randn(1, c, -(-40 // s), -(-56 // s), generator=g).to(DEV) for c, s in
+          ((64, 2), (128, 4), (256, 8), (512, 16))]
+    gt = (torch.rand(1, 1, 40, 56, generator=g) * 80).to(DEV)
+    noise = torch.randn(1, 16, 20, 28, generator=g).to(DEV)
+    a = vis(fp, gt, gt > 0, gt_depth_map=gt, noise=noise)
+    base.eval_ddim_loss = True
+    b = base(fp, gt, gt > 0, gt_depth_map=gt, noise=noise)
+    assert len(a["pred_inter"]) == 5 and a["pred_inter"][0].shape == (1, 1, 40, 56)
+    assert torch.allclose(vis.last_latent, base.last_latent, rtol=1e-5, atol=1e-4)
+    assert b["ddim_loss"].dim() == 0 and torch.isfinite(b["ddim_loss"]) and b["ddim_loss"] > 0
+
+
+def test_range_overflow_is_reported_not_silent():
+    head = _res_head(2).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    cond = torch.full((1, 256, 16, 32), 1.0e4)  # 1e4 * 16 > fp16 max
+    noise = torch.randn(1, 16, 16, 32, generator=g)
+    eng = head._engine(1, (16, 32), (16, 32), DEV)
+    eng.denoise_decode(cond.to(DEV), noise.to(DEV))
+    with pytest.raises(dd.EngineError, match="DD_ERR_RANGE"):
+        eng.poll_status()
+
+
+def test_weights_are_repacked_after_load_state_dict():
+    head = _res_head(3).to(DEV)
+    other = _res_head(3, seed=8).to(DEV)
+    g = torch.Generator().manual_seed(2)
+    cond, noise = torch.randn(1, 256, 16, 32, generator=g).abs().to(DEV), torch.randn(1, 16, 16, 32, generator=g).to(DEV)
+    eng = head._engine(1, (16, 32), (16, 32), DEV)
+    d1 = eng.denoise_decode(cond, noise)[0].clone()
+    head.load_state_dict(other.state_dict())
+    eng2 = head._engine(1, (16, 32), (16, 32), DEV)
+    assert eng2 is eng
+    d2 = eng2.denoise_decode(cond, noise)[0]
+    d3 = other._engine(1, (16, 32), (16, 32), DEV).denoise_decode(cond, noise)[0]
+    assert not torch.equal(d1, d2) and torch.equal(d2, d3)
+
+
+def test_host_buffer_end_to_end_call():
+    """The call a user makes (reference src/main.py:456-470): host sample -> .cuda() -> net(sample) -> host."""
+    g = helpers.load_golden("g_res18_ragged")
+    m = helpers.build_mirror(g["family"], g["T"]).to(DEV)
+    sample = restate.synthetic_sample(g["B"], g["H"], g["W"], configs.SEED_INPUTS)
+    sample["noise"] = restate.synthetic_noise(g["B"], g["H"], g["W"], configs.SEED_NOISE)
+    pinned = {k: v.pin_memory() for k, v in sample.items()}
+    with torch.no_grad():
+        out = m({k: v.to(DEV, non_blocking=True) for k, v in pinned.items()})
+    pred = out["pred"].cpu()
+    ref = torch.from_numpy(g["z"]["pred"])
+    z_ref = torch.from_numpy(g["z"]["logits"])
+    rel = (pred - ref).abs() / ref.abs().clamp_min(1e-6)
+    assert rel[z_ref.abs() < 10].max().item() < TOL
