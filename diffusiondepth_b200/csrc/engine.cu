@@ -87,16 +87,32 @@ int shape_id(int cin, int cout) {
 }
 
 template <int CIN, int COUT, int BK, int EPI>
+cudaError_t configure_umma() {
+  using C = dd::ConvCfg<CIN, COUT, BK>;
+  return cudaFuncSetAttribute(dd::conv3x3_umma_kernel<CIN, COUT, BK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              C::SMEM_BYTES);
+}
+template <int CIN, int COUT, int BK>
+cudaError_t configure_umma_all_epi() {
+  cudaError_t e;
+  if ((e = configure_umma<CIN, COUT, BK, dd::EPI_F32_STATS>()) != cudaSuccess) return e;
+  if ((e = configure_umma<CIN, COUT, BK, dd::EPI_SPLIT>()) != cudaSuccess) return e;
+  return configure_umma<CIN, COUT, BK, dd::EPI_F32>();
+}
+cudaError_t configure_all_kernels() {
+  cudaError_t e;
+  if ((e = configure_umma_all_epi<16, 64, 16>()) != cudaSuccess) return e;
+  if ((e = configure_umma_all_epi<64, 256, 32>()) != cudaSuccess) return e;
+  if ((e = configure_umma_all_epi<256, 256, 32>()) != cudaSuccess) return e;
+  if ((e = configure_umma_all_epi<256, 64, 64>()) != cudaSuccess) return e;
+  return configure_umma_all_epi<64, 16, 64>();
+}
+
+template <int CIN, int COUT, int BK, int EPI>
 cudaError_t launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                         const CUtensorMap& b_lo, const dd::ConvArgs& args, int sm_count, cudaStream_t st) {
   using C = dd::ConvCfg<CIN, COUT, BK>;
-  auto kern = dd::conv3x3_umma_kernel<CIN, COUT, BK, EPI>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  auto kern = dd::conv3x3_umma_kernel<CIN, COUT, BK, EPI>;  // smem attribute set in configure_all_kernels()
   int grid = args.num_tiles < sm_count ? args.num_tiles : sm_count;
   kern<<<grid, 256, C::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, args);
   return cudaGetLastError();
@@ -151,6 +167,7 @@ struct dd_engine {
   int* status = nullptr;
   // graph
   cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
   int64_t launches = 0;
   int* status_host = nullptr;  // pinned
 };
@@ -190,25 +207,28 @@ Geom geom_of(const dd_config& c) {
   return g;
 }
 
+// Lay the workspace out.  With base == nullptr only the size is computed (the engine's views are untouched).
 size_t carve(dd_engine* e, void* base) {
   const Geom g = geom_of(e->cfg);
   const size_t BP = static_cast<size_t>(g.B) * g.P;
   Carver c{reinterpret_cast<uint8_t*>(base)};
-  e->status = c.take<int>(16);
-  e->x32 = c.take<float>(BP * 16);
-  e->xs_hi = c.take<__half>(BP * 16);
-  e->xs_lo = c.take<__half>(BP * 16);
-  e->Y = c.take<float>(BP * 256);
+  dd_engine tmp_views;  // scratch target when only sizing
+  dd_engine* v = base ? e : &tmp_views;
+  v->status = c.take<int>(16);
+  v->x32 = c.take<float>(BP * 16);
+  v->xs_hi = c.take<__half>(BP * 16);
+  v->xs_lo = c.take<__half>(BP * 16);
+  v->Y = c.take<float>(BP * 256);
   for (int i = 0; i < 2; ++i) {
-    e->S_hi[i] = c.take<__half>(BP * 256);
-    e->S_lo[i] = c.take<__half>(BP * 256);
+    v->S_hi[i] = c.take<__half>(BP * 256);
+    v->S_lo[i] = c.take<__half>(BP * 256);
   }
-  e->cond = c.take<float>(static_cast<size_t>(g.B) * e->cfg.cond_h * e->cfg.cond_w * 256);
+  v->cond = c.take<float>(static_cast<size_t>(g.B) * e->cfg.cond_h * e->cfg.cond_w * 256);
   for (int i = 0; i < 4; ++i) {
-    e->stats[i] = c.take<float>(static_cast<size_t>(g.tiles) * 8);
-    e->mr[i] = c.take<float>(static_cast<size_t>(g.B) * 8);
+    v->stats[i] = c.take<float>(static_cast<size_t>(g.tiles) * 8);
+    v->mr[i] = c.take<float>(static_cast<size_t>(g.B) * 8);
   }
-  e->temb_sel = c.take<float>(static_cast<size_t>(g.B) * 256);
+  v->temb_sel = c.take<float>(static_cast<size_t>(g.B) * 256);
   return align_up(c.off, 1024);
 }
 
@@ -503,9 +523,14 @@ int dd_create(const dd_config* cfg, dd_handle* out) {
   dd_engine* e = new dd_engine();
   e->cfg = *cfg;
   e->sm_count = prop.multiProcessorCount;
-  if (cudaMallocHost(&e->status_host, 64) != cudaSuccess) {
+  if (cudaMallocHost(&e->status_host, 64) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      configure_all_kernels() != cudaSuccess) {
+    std::string msg = std::string("engine setup failed: ") + cudaGetErrorString(cudaGetLastError());
+    if (e->status_host) cudaFreeHost(e->status_host);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
     delete e;
-    return fail(DD_ERR_CUDA, "cudaMallocHost failed");
+    return fail(DD_ERR_CUDA, msg);
   }
   *out = e;
   return DD_OK;
@@ -517,6 +542,7 @@ int dd_destroy(dd_handle h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (void* p : h->owned) cudaFree(p);
   if (h->status_host) cudaFreeHost(h->status_host);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
   return DD_OK;
 }
@@ -679,11 +705,11 @@ int dd_denoise_decode(dd_handle h, const float* cond, const float* noise, float*
     if (!h->graph_exec) {
       cudaGraph_t graph = nullptr;
       const int64_t before = h->launches;
-      CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
       rc = DD_OK;
       for (int i = 0; i < T && rc == DD_OK; ++i)
-        rc = run_step(h, h->temb + h->ts[i] * 256, 0, h->cx[i], h->ce[i], nullptr, st);
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        rc = run_step(h, h->temb + h->ts[i] * 256, 0, h->cx[i], h->ce[i], nullptr, h->cap_stream);
+      cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
       h->launches = before;
       if (rc != DD_OK) {
         if (graph) cudaGraphDestroy(graph);

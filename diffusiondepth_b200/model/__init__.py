@@ -12,3 +12,8 @@ def get(args):
             f"{model_name}: only the DiffusionDepth model (Diffusion_DCbase_) is served by the B200 engine; "
             "NLSPN and the DCN extension are out of scope (DESIGN.md)") from e
     return getattr(module, model_name)
+
+
+# importing the package registers the codec and head classes (HEADS / DEPTH_TRANSFORM lookups need them)
+from .ops import depth_transform as _codec  # noqa: E402,F401
+from . import head as _head  # noqa: E402,F401
