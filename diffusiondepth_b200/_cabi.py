@@ -18,6 +18,11 @@ class DDConfig(C.Structure):
                 ("flags", C.c_int32)]
 
 
+class DDProducerConfig(C.Structure):
+    _fields_ = [("num_levels", C.c_int32), ("channels", C.c_int32 * 4), ("heights", C.c_int32 * 4),
+                ("widths", C.c_int32 * 4), ("has_neck", C.c_int32)]
+
+
 ABI_VERSION = 1
 VARIANT_RES, VARIANT_SWIN = 0, 1
 FLAG_CUDA_GRAPH, FLAG_SIMT_CONV, FLAG_CHECK_RANGE = 1, 2, 4
@@ -34,6 +39,9 @@ SIGNATURES = {
     "dd_set_schedule": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.c_int32]),
     "dd_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "dd_enable_producers": (C.c_int, [C.c_void_p, C.POINTER(DDProducerConfig)]),
+    "dd_build_condition": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t,
+                                     C.c_void_p]),
     "dd_denoise_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "dd_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p,

@@ -1,0 +1,318 @@
+// General stride-1 convolution (1x1 or 3x3, zero pad) + per-channel shift (+ReLU, +addend) on tcgen05, used
+// for the step-invariant producers: HAHI neck (1x1 / 3x3 ConvModules with eval-BN folded, channel-concatenated
+// inputs) and the FPN (3x3 laterals, 2x2/s2 transposed convs as a 1x1 GEMM with a pixel-shuffle epilogue).
+// Same machinery as conv3x3_umma_kernel (3-pass fp16 hi/lo split, TMA-staged swizzled tiles, TMEM double
+// buffer, warp-specialised persistent CTA) with runtime shapes:
+//   M = 128 pixels (8x16 patch), N tile = NT output channels, K = taps x (cin0 + cin1) in chunks of 32 channels,
+//   the K range may be fed from two source tensors (torch.cat([a, b], dim=1) never materialises).
+// Replaces (reference): mmcv ConvModule calls in src/model/necks/hahi.py:165-276 and the FPN in
+// src/model/head/ddim_depth_estimate_res_swin_addHAHI.py:112-122.
+#pragma once
+#include "conv_umma.cuh"
+
+namespace dd {
+
+struct GenConvArgs {
+  int B, H, W;
+  int tiles_x, tiles_y, m_tiles, n_tiles;
+  int kc0, kc1;       // 32-channel chunks taken from source 0, then source 1
+  int taps;           // 1 (1x1) or 9 (3x3, pad 1)
+  int cout;           // total output channels (n_tiles * NT)
+  const float* shift; // [cout] bias / folded BN shift
+  float acc_scale;
+  int relu;
+  int shuffle;        // 1: ConvTranspose2d(k=2,s=2): channel n = q*(cout/4)+c goes to pixel (2y+q/2, 2x+q%2), channel c
+  float* y32;         // optional fp32 NHWC output
+  const float* add32; // optional fp32 NHWC addend (indexed like y32), added after the ReLU
+  __half* out_hi;     // optional fp16 hi/lo planes of the output (indexed like y32)
+  __half* out_lo;
+  float split_scale;
+  int* status;
+};
+
+template <int NT>
+struct GenCfg {
+  static constexpr int BK = 32;
+  static constexpr int ROW_BYTES = BK * 2;
+  static constexpr int A_BYTES = TILE_M * ROW_BYTES;  // 8 KB per plane
+  static constexpr int B_BYTES = NT * ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(NT % 32 == 0 && NT <= 256 && 2 * NT <= 512, "bad N tile");
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_constant__ CUtensorMap tmA0_lo,
+                    const __grid_constant__ CUtensorMap tmA1_hi, const __grid_constant__ CUtensorMap tmA1_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const GenConvArgs p) {
+  using C = GenCfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kc_total = p.kc0 + p.kc1;
+  const int k_iters = p.taps * kc_total;
+  const int num_work = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0_hi);
+    tma_prefetch_desc(&tmA0_lo);
+    tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&tmB_lo);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int nt = work % p.n_tiles, mt = work / p.n_tiles;  // n fastest: neighbours share the A patch in L2
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int dy = p.taps == 9 ? tap / 3 - 1 : 0, dx = p.taps == 9 ? tap % 3 - 1 : 0;
+        for (int kc = 0; kc < kc_total; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* s = stage_ptr(stage);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if (kc < p.kc0) {
+            tma_load_4d(s, &tmA0_hi, &full_bar[stage], kc * C::BK, x0 + dx, y0 + dy, img);
+            tma_load_4d(s + C::A_BYTES, &tmA0_lo, &full_bar[stage], kc * C::BK, x0 + dx, y0 + dy, img);
+          } else {
+            tma_load_4d(s, &tmA1_hi, &full_bar[stage], (kc - p.kc0) * C::BK, x0 + dx, y0 + dy, img);
+            tma_load_4d(s + C::A_BYTES, &tmA1_lo, &full_bar[stage], (kc - p.kc0) * C::BK, x0 + dx, y0 + dy, img);
+          }
+          tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * C::BK, nt * NT, tap);
+          tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * C::BK, nt * NT, tap);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_f16(TILE_M, NT);
+    int stage = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    int buf = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * NT);
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa_hi = smem_u32(stage_ptr(stage));
+        const uint32_t sa_lo = sa_hi + C::A_BYTES;
+        const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
+        const uint32_t sb_lo = sb_hi + C::B_BYTES;
+#pragma unroll
+        for (int k = 0; k < C::BK / 16; ++k) {
+          const uint64_t a_hi = umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES);
+          const uint64_t a_lo = umma_smem_desc(sa_lo + k * 32, C::ROW_BYTES);
+          const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
+          const uint64_t b_lo = umma_smem_desc(sb_lo + k * 32, C::ROW_BYTES);
+          umma_f16(d_tmem, a_lo, b_hi, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+          umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (it == k_iters - 1) umma_commit(&tfull_bar[buf]);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc_phase ^= (1u << buf);
+      buf ^= 1;
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int r = m >> 4, c = m & 15;
+    uint32_t full_phase = 0;
+    int buf = 0;
+    bool overflow = false;
+    const int cq = p.cout >> 2;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int nt = work % p.n_tiles, mt = work / p.n_tiles;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
+      const int x = tx * TILE_W + c, y = ty * TILE_H + r;
+      const bool valid = (x < p.W) && (y < p.H);
+      mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
+      full_phase ^= (1u << buf);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch0 = 0; ch0 < NT; ch0 += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * NT + ch0), rr);
+        tmem_ld_wait();
+        if (!valid) continue;
+        const int n0 = nt * NT + ch0;
+        size_t o;  // element offset of channel n0's destination
+        if (p.shuffle) {
+          const int sub = n0 / cq, cc = n0 - sub * cq;
+          o = ((static_cast<size_t>(img) * (2 * p.H) + (2 * y + (sub >> 1))) * (2 * p.W) + (2 * x + (sub & 1))) * cq + cc;
+        } else {
+          o = ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout + n0;
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = fmaf(__uint_as_float(rr[j]), p.acc_scale, __ldg(p.shift + n0 + j));
+          v[j] = p.relu ? fmaxf(t, 0.f) : t;
+        }
+        if (p.add32) {
+          const float4* a4 = reinterpret_cast<const float4*>(p.add32 + o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = a4[j];
+            v[4 * j] += t.x;
+            v[4 * j + 1] += t.y;
+            v[4 * j + 2] += t.z;
+            v[4 * j + 3] += t.w;
+          }
+        }
+        if (p.y32) {
+          float4* d4 = reinterpret_cast<float4*>(p.y32 + o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (p.out_hi) {
+          __align__(16) __half hi[32];
+          __align__(16) __half lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = v[j] * p.split_scale;
+            overflow |= (fabsf(s) > 60000.f);
+            hi[j] = __float2half_rn(s);
+            lo[j] = __float2half_rn(s - __half2float(hi[j]));
+          }
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dh[j] = reinterpret_cast<const uint4*>(hi)[j];
+            dl[j] = reinterpret_cast<const uint4*>(lo)[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      buf ^= 1;
+    }
+    if (overflow) atomicOr(p.status, 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// fp32 NCHW [B][C][P] -> fp16 hi/lo NHWC planes [B][P][C] (scaled): backbone feature maps entering the neck
+__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
+                                          int C, int P, float scale, int* status) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = in + static_cast<size_t>(b) * C * P;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, pp = p0 + threadIdx.x;
+    t[i][threadIdx.x] = (c < C && pp < P) ? src[static_cast<size_t>(c) * P + pp] : 0.f;
+  }
+  __syncthreads();
+  bool ov = false;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int pp = p0 + i, c = c0 + threadIdx.x;
+    if (pp < P && c < C) {
+      const float s = t[threadIdx.x][i] * scale;
+      ov |= fabsf(s) > 60000.f;
+      const __half h = __float2half_rn(s);
+      const size_t o = (static_cast<size_t>(b) * P + pp) * C + c;
+      hi[o] = h;
+      lo[o] = __float2half_rn(s - __half2float(h));
+    }
+  }
+  if (ov) atomicOr(status, 1);
+}
+
+// w [COUT][CIN][kh][kw] (conv) -> scaled fp16 hi/lo [tap][COUT][CIN] with a per-output-channel factor folded in
+// (eval-BatchNorm scale).  transposed=1: w is ConvTranspose2d(k=2,s=2) [CIN][CO][2][2] and becomes a 1-tap
+// [4*CO][CIN] matrix, row n = (ky*2+kx)*CO + co.
+__global__ void pack_gen_weight_kernel(const float* __restrict__ w, const float* __restrict__ ch_scale,
+                                       __half* __restrict__ hi, __half* __restrict__ lo, int cout, int cin, int taps,
+                                       int transposed, float scale) {
+  const int n = cout * cin * taps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float v, f;
+    size_t o;
+    if (!transposed) {
+      const int tap = i % taps, ci = (i / taps) % cin, co = i / (taps * cin);
+      v = w[i];
+      f = ch_scale ? ch_scale[co] : 1.f;
+      o = (static_cast<size_t>(tap) * cout + co) * cin + ci;
+    } else {
+      const int co4 = cout / 4;  // here cout = 4*CO, taps == 1, n = cin*CO*4
+      const int kk = i % 4, co = (i / 4) % co4, ci = i / (4 * co4);
+      v = w[i];
+      f = ch_scale ? ch_scale[co] : 1.f;
+      o = (static_cast<size_t>(kk) * co4 + co) * cin + ci;
+    }
+    const float s = v * f * scale;
+    const __half h = __float2half_rn(s);
+    hi[o] = h;
+    lo[o] = __float2half_rn(s - __half2float(h));
+  }
+}
+// max |w * ch_scale[co]| for the power-of-two weight scale
+__global__ void absmax_scaled_kernel(const float* __restrict__ w, const float* __restrict__ ch_scale, int n, int per_co,
+                                     int co_mod, int transposed, float* __restrict__ out) {
+  __shared__ float sm[256];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int co = transposed ? (i / 4) % co_mod : i / per_co;
+    m = fmaxf(m, fabsf(w[i] * (ch_scale ? ch_scale[co] : 1.f)));
+  }
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sm[0];
+}
+
+}  // namespace dd

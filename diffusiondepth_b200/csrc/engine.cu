@@ -14,6 +14,7 @@
 
 #include "../../include/dd_engine.h"
 #include "kernels.cuh"
+#include "convgen.cuh"
 
 namespace {
 
@@ -75,6 +76,19 @@ int make_w_map(CUtensorMap* m, const __half* base, int cout, int cin, int bk) {
   return DD_OK;
 }
 
+// general conv weights: [taps][COUT][CIN] fp16; box = {32, NT, 1}
+int make_wgen_map(CUtensorMap* m, const __half* base, int cout, int cin, int taps, int nt) {
+  cuuint64_t gdim[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps};
+  cuuint64_t gstr[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
+  cuuint32_t box[3] = {32, (cuuint32_t)nt, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(gen weight) failed: " + std::to_string((int)r));
+  return DD_OK;
+}
+
 // ---- conv shapes served by the engine
 struct ShapeInfo {
   int cin, cout, bk;
@@ -105,7 +119,11 @@ cudaError_t configure_all_kernels() {
   if ((e = configure_umma_all_epi<64, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<256, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<256, 64, 64>()) != cudaSuccess) return e;
-  return configure_umma_all_epi<64, 16, 64>();
+  if ((e = configure_umma_all_epi<64, 16, 64>()) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::GenCfg<256>::SMEM_BYTES)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dd::convgen_umma_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              dd::GenCfg<192>::SMEM_BYTES);
 }
 
 template <int CIN, int COUT, int BK, int EPI>
@@ -140,6 +158,29 @@ struct Raw {
   std::vector<int64_t> shape;
 };
 
+// One producer convolution (neck / FPN): eval-BN folded into the weights (scale) and `shift`.
+struct GenLayer {
+  int cin = 0, cout = 0, taps = 1, nt = 256, relu = 1, shuffle = 0;
+  __half* w_hi = nullptr;
+  __half* w_lo = nullptr;
+  float* shift = nullptr;
+  float wscale = 1.f;
+  CUtensorMap mb_hi, mb_lo;
+};
+struct Planes {
+  __half* hi = nullptr;
+  __half* lo = nullptr;
+};
+struct Producers {
+  bool enabled = false, ready = false, neck = false;
+  int nlev = 0;
+  int C[4] = {0, 0, 0, 0}, H[4] = {0, 0, 0, 0}, W[4] = {0, 0, 0, 0};
+  GenLayer lat[4], proj[4], fus[4], fl[4], fu[3];
+  Planes F[4], L[4], P[4], O[4], XP[4];
+  float* X[4] = {nullptr, nullptr, nullptr, nullptr};   // fp32 NHWC FPN outputs (X[0] aliases the loop's cond)
+  float* UP[3] = {nullptr, nullptr, nullptr};           // fp32 NHWC upsampled maps at level i
+};
+
 }  // namespace
 
 struct dd_engine {
@@ -166,6 +207,8 @@ struct dd_engine {
   __half *xs_hi = nullptr, *xs_lo = nullptr, *S_hi[2] = {}, *S_lo[2] = {};
   int* status = nullptr;
   // graph
+  Producers prod;
+  bool cond_ready = false;  // dd_build_condition has filled `cond` for the next dd_denoise_decode(cond = NULL)
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
   int64_t launches = 0;
@@ -229,6 +272,26 @@ size_t carve(dd_engine* e, void* base) {
     v->mr[i] = c.take<float>(static_cast<size_t>(g.B) * 8);
   }
   v->temb_sel = c.take<float>(static_cast<size_t>(g.B) * 256);
+  if (e->prod.enabled) {
+    const Producers& pc = e->prod;
+    Producers* pv = &v->prod;
+    for (int i = 0; i < pc.nlev; ++i) {
+      const size_t px = static_cast<size_t>(g.B) * pc.H[i] * pc.W[i];
+      auto planes = [&](Planes& pl, size_t ch) {
+        pl.hi = c.take<__half>(px * ch);
+        pl.lo = c.take<__half>(px * ch);
+      };
+      planes(pv->F[i], pc.C[i]);
+      if (pc.neck) {
+        planes(pv->L[i], pc.C[i]);
+        planes(pv->P[i], 512);
+        planes(pv->O[i], pc.C[i]);
+      }
+      planes(pv->XP[i], 256);
+      pv->X[i] = (i == 0) ? v->cond : c.take<float>(px * 256);
+      if (i < pc.nlev - 1) pv->UP[i] = c.take<float>(px * 256);
+    }
+  }
   return align_up(c.off, 1024);
 }
 
@@ -495,6 +558,149 @@ int pack_layer(dd_engine* e, ConvLayer& L, const float* w, const float* b, int c
   return DD_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ producers
+constexpr float kProdScale = 16.f;  // fp16-split pre-scale of every producer activation
+
+// Fold eval-BN (prefix.{weight,bias,running_mean,running_var}) into per-channel (scale, shift) on the host.
+int bn_fold(dd_engine* e, const std::string& bn, int ch, std::vector<float>& scale, std::vector<float>& shift,
+            cudaStream_t st) {
+  const char* parts[4] = {".weight", ".bias", ".running_mean", ".running_var"};
+  std::vector<float> v[4];
+  for (int i = 0; i < 4; ++i) {
+    const Raw* r = find(e, bn + parts[i]);
+    if (!r) return fail(DD_ERR_INVALID, "missing weights: " + bn + parts[i]);
+    v[i].resize(ch);
+    CUDA_TRY(cudaMemcpyAsync(v[i].data(), r->ptr, ch * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  scale.resize(ch);
+  shift.resize(ch);
+  for (int c = 0; c < ch; ++c) {
+    const double sc = static_cast<double>(v[0][c]) / sqrt(static_cast<double>(v[3][c]) + 1e-5);
+    scale[c] = static_cast<float>(sc);
+    shift[c] = static_cast<float>(static_cast<double>(v[1][c]) - static_cast<double>(v[2][c]) * sc);
+  }
+  return DD_OK;
+}
+
+// conv weight key `wkey` ([cout][cin][k][k], or ConvT [cin][co][2][2] when transposed) + BN `bnkey`
+int pack_gen(dd_engine* e, GenLayer& L, const std::string& wkey, const std::string& bnkey, int cin, int cout_conv,
+             int taps, bool transposed, cudaStream_t st, float* scratch) {
+  const Raw* w = find(e, wkey);
+  if (!w) return fail(DD_ERR_INVALID, "missing weights: " + wkey);
+  const int k = taps == 9 ? 3 : (transposed ? 2 : 1);
+  std::vector<int64_t> want = transposed ? std::vector<int64_t>{cin, cout_conv, 2, 2}
+                                         : std::vector<int64_t>{cout_conv, cin, k, k};
+  if (w->shape != want) return fail(DD_ERR_INVALID, "weight shape mismatch: " + wkey);
+  std::vector<float> scale, shift;
+  int rc;
+  if ((rc = bn_fold(e, bnkey, cout_conv, scale, shift, st))) return rc;
+  L.cin = cin;
+  L.taps = transposed ? 1 : taps;
+  L.cout = transposed ? 4 * cout_conv : cout_conv;
+  L.shuffle = transposed ? 1 : 0;
+  L.relu = 1;
+  L.nt = (L.cout % 256 == 0) ? 256 : 192;
+  if (L.cout % L.nt != 0 || cin % 32 != 0) return fail(DD_ERR_UNSUPPORTED, "producer conv channels not tileable: " + wkey);
+  const size_t n = static_cast<size_t>(L.cout) * cin * L.taps;
+  float *d_scale = nullptr;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_hi), n * 2))) return rc;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_lo), n * 2))) return rc;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.shift), L.cout * 4))) return rc;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&d_scale), cout_conv * 4))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_scale, scale.data(), cout_conv * 4, cudaMemcpyHostToDevice, st));
+  std::vector<float> shift_full(L.cout);
+  for (int i = 0; i < L.cout; ++i) shift_full[i] = shift[i % cout_conv];
+  CUDA_TRY(cudaMemcpyAsync(L.shift, shift_full.data(), L.cout * 4, cudaMemcpyHostToDevice, st));
+  const int nraw = static_cast<int>(static_cast<size_t>(cout_conv) * cin * (transposed ? 4 : taps));
+  dd::absmax_scaled_kernel<<<1, 256, 0, st>>>(w->ptr, d_scale, nraw, cin * taps, cout_conv, transposed ? 1 : 0, scratch);
+  float amax = 0.f;
+  CUDA_TRY(cudaMemcpyAsync(&amax, scratch, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  L.wscale = (amax > 0.f && isfinite(amax)) ? exp2f(floorf(log2f(32768.f / amax)) - 1.f) : 1.f;
+  dd::pack_gen_weight_kernel<<<256, 256, 0, st>>>(w->ptr, d_scale, L.w_hi, L.w_lo, L.cout, cin, L.taps,
+                                                  transposed ? 1 : 0, L.wscale);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if ((rc = make_wgen_map(&L.mb_hi, L.w_hi, L.cout, cin, L.taps, L.nt))) return rc;
+  if ((rc = make_wgen_map(&L.mb_lo, L.w_lo, L.cout, cin, L.taps, L.nt))) return rc;
+  return DD_OK;
+}
+
+int pack_producers(dd_engine* e, cudaStream_t st, float* scratch) {
+  Producers& p = e->prod;
+  int rc;
+  for (int i = 0; i < p.nlev; ++i) {
+    const std::string si = std::to_string(i);
+    if (p.neck) {
+      const std::string h = "hahineck.";
+      if ((rc = pack_gen(e, p.lat[i], h + "lateral_convs." + si + ".conv.weight", h + "lateral_convs." + si + ".bn",
+                         p.C[i], p.C[i], 1, false, st, scratch))) return rc;
+      const std::string pj = i == 0 ? h + "conv_proj.0" : h + "trans_proj." + std::to_string(i - 1);
+      const std::string fs = i == 0 ? h + "conv_fusion.0" : h + "trans_fusion." + std::to_string(i - 1);
+      if ((rc = pack_gen(e, p.proj[i], pj + ".conv.weight", pj + ".bn", p.C[i], 512, 1, false, st, scratch))) return rc;
+      if ((rc = pack_gen(e, p.fus[i], fs + ".conv.weight", fs + ".bn", p.C[i] + 512, p.C[i], 9, false, st, scratch))) return rc;
+    }
+    if ((rc = pack_gen(e, p.fl[i], "conv_lateral." + si + ".0.weight", "conv_lateral." + si + ".1", p.C[i], 256, 9, false,
+                       st, scratch))) return rc;
+    if (i < p.nlev - 1)
+      if ((rc = pack_gen(e, p.fu[i], "conv_up." + si + ".0.weight", "conv_up." + si + ".1", 256, 256, 1, true, st,
+                         scratch))) return rc;
+  }
+  p.ready = true;
+  return DD_OK;
+}
+
+int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Planes& a1, int c1, int H, int W,
+            float* y32, const float* add32, const Planes* out, cudaStream_t st) {
+  const int B = e->cfg.batch;
+  dd::GenConvArgs a;
+  a.B = B;
+  a.H = H;
+  a.W = W;
+  a.tiles_x = (W + dd::TILE_W - 1) / dd::TILE_W;
+  a.tiles_y = (H + dd::TILE_H - 1) / dd::TILE_H;
+  a.m_tiles = a.tiles_x * a.tiles_y * B;
+  a.n_tiles = L.cout / L.nt;
+  a.kc0 = c0 / 32;
+  a.kc1 = c1 / 32;
+  a.taps = L.taps;
+  a.cout = L.cout;
+  a.shift = L.shift;
+  a.acc_scale = 1.f / (kProdScale * L.wscale);
+  a.relu = L.relu;
+  a.shuffle = L.shuffle;
+  a.y32 = y32;
+  a.add32 = add32;
+  a.out_hi = out ? out->hi : nullptr;
+  a.out_lo = out ? out->lo : nullptr;
+  a.split_scale = kProdScale;
+  a.status = e->status;
+  if (c0 + c1 != L.cin) return fail(DD_ERR_INVALID, "producer conv: source channels do not match the layer");
+  CUtensorMap m0h, m0l, m1h, m1l;
+  int rc;
+  if ((rc = make_act_map(&m0h, a0.hi, B, H, W, c0, 32))) return rc;
+  if ((rc = make_act_map(&m0l, a0.lo, B, H, W, c0, 32))) return rc;
+  if (c1 > 0) {
+    if ((rc = make_act_map(&m1h, a1.hi, B, H, W, c1, 32))) return rc;
+    if ((rc = make_act_map(&m1l, a1.lo, B, H, W, c1, 32))) return rc;
+  } else {
+    m1h = m0h;
+    m1l = m0l;
+  }
+  const int work = a.m_tiles * a.n_tiles;
+  const int grid = work < e->sm_count ? work : e->sm_count;
+  if (L.nt == 256)
+    dd::convgen_umma_kernel<256><<<grid, 256, dd::GenCfg<256>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
+  else
+    dd::convgen_umma_kernel<192><<<grid, 256, dd::GenCfg<192>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
+  e->launches++;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("convgen launch: ") + cudaGetErrorString(err));
+  return DD_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -561,7 +767,8 @@ static const char* kKeys[] = {
 
 int dd_set_weight(dd_handle h, const char* name, const float* dev_ptr, const int64_t* shape, int32_t ndim) {
   if (!h || !name || !dev_ptr || ndim < 0 || ndim > 4) return fail(DD_ERR_INVALID, "bad argument");
-  bool known = false;
+  bool known = strncmp(name, "hahineck.", 9) == 0 || strncmp(name, "conv_lateral.", 13) == 0 ||
+               strncmp(name, "conv_up.", 8) == 0;  // step-invariant producers (optional, dd_enable_producers)
   for (const char* k : kKeys) known |= (strcmp(k, name) == 0);
   if (!known) return fail(DD_ERR_INVALID, std::string("unknown weight key: ") + name);
   Raw r;
@@ -652,6 +859,9 @@ int dd_finalize_weights(dd_handle h, void* cuda_stream) {
   CUDA_TRY(cudaMemcpyAsync(h->dec_wc, wc_f.data(), wc_f.size() * 4, cudaMemcpyHostToDevice, st));
   h->dec_bc = bc[0];
   CUDA_TRY(cudaStreamSynchronize(st));
+  h->prod.ready = false;
+  if (h->prod.enabled)
+    if ((rc = pack_producers(h, st, scratch))) return rc;
   h->weights_ready = true;
   return DD_OK;
 }
@@ -686,7 +896,8 @@ static int poll_status(dd_handle h, cudaStream_t st) {
 
 int dd_denoise_decode(dd_handle h, const float* cond, const float* noise, float* latent_out, float* logit_out,
                       float* depth_out, void* workspace, size_t workspace_bytes, void* cuda_stream) {
-  if (!h || !cond || !noise || !depth_out) return fail(DD_ERR_INVALID, "null argument");
+  if (!h || !noise || !depth_out) return fail(DD_ERR_INVALID, "null argument");
+  if (!cond && !h->cond_ready) return fail(DD_ERR_INVALID, "cond is NULL but dd_build_condition has not run");
   if (!h->weights_ready) return fail(DD_ERR_INVALID, "dd_finalize_weights has not been called");
   if (static_cast<int>(h->ts.size()) != h->cfg.num_inference_steps) return fail(DD_ERR_INVALID, "dd_set_schedule has not been called");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
@@ -694,12 +905,16 @@ int dd_denoise_decode(dd_handle h, const float* cond, const float* noise, float*
   int rc;
   if ((rc = bind_workspace(h, workspace, workspace_bytes))) return rc;
   const Geom g = geom_of(h->cfg);
-  h->launches = 0;
-  CUDA_TRY(cudaMemsetAsync(h->status, 0, 64, st));
-  if ((rc = transpose_in(cond, h->cond, g.B, 256, h->cfg.cond_h * h->cfg.cond_w, st))) return rc;
+  if (cond) {
+    h->launches = 0;
+    CUDA_TRY(cudaMemsetAsync(h->status, 0, 64, st));
+    if ((rc = transpose_in(cond, h->cond, g.B, 256, h->cfg.cond_h * h->cfg.cond_w, st))) return rc;
+    h->launches += 1;
+  }  // else: dd_build_condition left the NHWC condition map (and the launch / status counters) in place
+  h->cond_ready = false;
   if ((rc = transpose_in(noise, h->x32, g.B, 16, g.P, st))) return rc;
   if ((rc = split_planes(h, h->x32, h->xs_hi, h->xs_lo, static_cast<size_t>(g.B) * g.P * 16, kXScale, st))) return rc;
-  h->launches += 3;
+  h->launches += 2;
   const int T = h->cfg.num_inference_steps;
   if (h->cfg.flags & DD_FLAG_CUDA_GRAPH) {
     if (!h->graph_exec) {
@@ -772,6 +987,87 @@ int dd_decode(dd_handle h, const float* latent, float* logit_out, float* depth_o
   const Geom g = geom_of(h->cfg);
   if ((rc = transpose_in(latent, h->x32, g.B, 16, g.P, st))) return rc;
   return run_decoder(h, logit_out, depth_out, st);
+}
+
+int dd_enable_producers(dd_handle h, const dd_producer_config* pc) {
+  if (!h || !pc) return fail(DD_ERR_INVALID, "null argument");
+  if (pc->num_levels < 2 || pc->num_levels > 4) return fail(DD_ERR_INVALID, "producers need 2..4 pyramid levels");
+  Producers p;
+  p.enabled = true;
+  p.neck = pc->has_neck != 0;
+  p.nlev = pc->num_levels;
+  for (int i = 0; i < p.nlev; ++i) {
+    p.C[i] = pc->channels[i];
+    p.H[i] = pc->heights[i];
+    p.W[i] = pc->widths[i];
+    if (p.C[i] % 32 != 0 || p.C[i] <= 0) return fail(DD_ERR_UNSUPPORTED, "feature channels must be multiples of 32");
+    if (p.neck && p.C[i] % 192 != 0) return fail(DD_ERR_UNSUPPORTED, "neck channel counts must tile by 192");
+    // the FPN's adaptive_avg_pool2d (reference head :121) is the identity only for exact 2x pyramids
+    if (i > 0 && (p.H[i - 1] != 2 * p.H[i] || p.W[i - 1] != 2 * p.W[i]))
+      return fail(DD_ERR_UNSUPPORTED, "native FPN needs an exact 2x pyramid (adaptive pooling would resample)");
+  }
+  if (p.H[0] != h->cfg.cond_h || p.W[0] != h->cfg.cond_w)
+    return fail(DD_ERR_INVALID, "level-0 feature size must equal the condition map size");
+  h->prod = p;
+  h->weights_ready = false;  // producer weights are packed by dd_finalize_weights
+  h->ws = nullptr;           // workspace layout changed
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  return DD_OK;
+}
+
+int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, void* workspace, size_t workspace_bytes,
+                       void* cuda_stream) {
+  if (!h || !feats) return fail(DD_ERR_INVALID, "null argument");
+  if (!h->prod.enabled || !h->weights_ready || !h->prod.ready)
+    return fail(DD_ERR_INVALID, "producers not enabled / weights not finalized");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc;
+  if ((rc = bind_workspace(h, workspace, workspace_bytes))) return rc;
+  Producers& p = h->prod;
+  const int B = h->cfg.batch;
+  CUDA_TRY(cudaMemsetAsync(h->status, 0, 64, st));
+  h->launches = 0;
+  for (int i = 0; i < p.nlev; ++i) {
+    if (!feats[i]) return fail(DD_ERR_INVALID, "null feature map");
+    const int P = p.H[i] * p.W[i];
+    dim3 grid((P + 31) / 32, (p.C[i] + 31) / 32, B), block(32, 8);
+    dd::nchw_to_nhwc_split_kernel<<<grid, block, 0, st>>>(feats[i], p.F[i].hi, p.F[i].lo, p.C[i], P, kProdScale, h->status);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  const Planes none;
+  for (int i = 0; i < p.nlev; ++i) {
+    if (!p.neck) {
+      p.O[i] = p.F[i];
+      continue;
+    }
+    // HAHI neck, attention gates off (reference necks/hahi.py:173-176, 226-250, 253-272)
+    if ((rc = run_gen(h, p.lat[i], p.F[i], p.C[i], none, 0, p.H[i], p.W[i], nullptr, nullptr, &p.L[i], st))) return rc;
+    if ((rc = run_gen(h, p.proj[i], p.L[i], p.C[i], none, 0, p.H[i], p.W[i], nullptr, nullptr, &p.P[i], st))) return rc;
+    if (i == 0) {  // cat([conv_proj(lat), lat])
+      if ((rc = run_gen(h, p.fus[i], p.P[i], 512, p.L[i], p.C[i], p.H[i], p.W[i], nullptr, nullptr, &p.O[i], st))) return rc;
+    } else {       // cat([lat, trans_proj(lat)])
+      if ((rc = run_gen(h, p.fus[i], p.L[i], p.C[i], p.P[i], 512, p.H[i], p.W[i], nullptr, nullptr, &p.O[i], st))) return rc;
+    }
+  }
+  // FPN top-down (reference head :112-122): x_i = relu(bn(conv3x3(O_i))) + relu(bn(convT2x2(x_{i+1})))
+  for (int i = p.nlev - 1; i >= 0; --i) {
+    const float* add = (i < p.nlev - 1) ? p.UP[i] : nullptr;
+    if ((rc = run_gen(h, p.fl[i], p.O[i], p.C[i], none, 0, p.H[i], p.W[i], p.X[i], add, i > 0 ? &p.XP[i] : nullptr, st)))
+      return rc;
+    if (i > 0)
+      if ((rc = run_gen(h, p.fu[i - 1], p.XP[i], 256, none, 0, p.H[i], p.W[i], p.UP[i - 1], nullptr, nullptr, st))) return rc;
+  }
+  h->cond_ready = true;
+  if (cond_out) {
+    if ((rc = transpose_out(h->cond, cond_out, B, 256, p.H[0] * p.W[0], st))) return rc;
+    h->launches++;
+  }
+  return DD_OK;
 }
 
 int64_t dd_last_launch_count(dd_handle h) { return h ? h->launches : 0; }

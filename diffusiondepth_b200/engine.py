@@ -71,10 +71,16 @@ class DenoiseEngine:
         self._h = h
         self._ws: Optional[torch.Tensor] = None
         self._keep = []  # fp32 contiguous copies handed to dd_set_weight must outlive finalize
+        self.producers = None
 
     # ---------------------------------------------------------------- setup
     def load_weights(self, tensors: Dict[str, torch.Tensor]):
         keys = DENOISER_KEYS + DECODER_KEYS + (FUSE_KEYS if self.variant == "swin" else ())
+        if self.producers is not None:
+            keys = keys + tuple(k for k in tensors if k.startswith(("hahineck.", "conv_lateral.", "conv_up."))
+                                and not k.endswith("num_batches_tracked") and tensors[k].dim() <= 4
+                                and not k.startswith(("hahineck.multi_att", "hahineck.self_attn",
+                                                      "hahineck.reference_points", "hahineck.level_embed")))
         self._keep = []
         for k in keys:
             if k not in tensors:
@@ -85,6 +91,17 @@ class DenoiseEngine:
             _cabi.check(self.lib.dd_set_weight(self._h, k.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
         _cabi.check(self.lib.dd_finalize_weights(self._h, C.c_void_p(self._stream())))
         self._keep = []
+
+    def enable_producers(self, channels, sizes, has_neck: bool):
+        """Run the HAHI neck (if any) + FPN natively too; call before load_weights.  `sizes`: [(h, w)] per level."""
+        pc = _cabi.DDProducerConfig()
+        pc.num_levels = len(channels)
+        for i, (c, (hh, ww)) in enumerate(zip(channels, sizes)):
+            pc.channels[i], pc.heights[i], pc.widths[i] = int(c), int(hh), int(ww)
+        pc.has_neck = 1 if has_neck else 0
+        _cabi.check(self.lib.dd_enable_producers(self._h, C.byref(pc)))
+        self.producers = (tuple(channels), tuple(tuple(s_) for s_ in sizes), bool(has_neck))
+        self._ws = None
 
     def set_schedule(self, timesteps, c_x, c_eps):
         n = len(timesteps)
@@ -110,17 +127,35 @@ class DenoiseEngine:
             raise EngineError(f"expected contiguous fp32 {tuple(shape)} on {self.device}, got {tuple(t.shape)} "
                               f"{t.dtype} {t.device}")
 
-    def denoise_decode(self, cond: torch.Tensor, noise: torch.Tensor, want_latent=False, want_logits=False):
-        """cond [B,256,hc,wc], noise [B,16,h,w] -> depth [B,1,2h,2w] (+ latent [B,16,h,w], logits)."""
+    def build_condition(self, feats, want_cond=False):
+        """Backbone feature maps (fp32 NCHW, finest first) -> condition map, natively (neck + FPN).  The result
+        stays inside the workspace for the next `denoise_decode(None, noise)`; `want_cond` also returns it."""
+        if self.producers is None:
+            raise EngineError("enable_producers() was not called")
+        chans, sizes, _ = self.producers
+        for f, c, hw in zip(feats, chans, sizes):
+            self._check_in(f, (self.batch, c, *hw))
+        ptrs = (C.c_void_p * 4)(*([f.data_ptr() for f in feats] + [0] * (4 - len(feats))))
+        cond = torch.empty(self.batch, 256, *self.cond_hw, device=self.device) if want_cond else None
+        ws = self._workspace()
+        _cabi.check(self.lib.dd_build_condition(self._h, ptrs, C.c_void_p(cond.data_ptr() if want_cond else 0),
+                                                C.c_void_p(self._aligned(ws)), ws.numel() - 1024,
+                                                C.c_void_p(self._stream())))
+        return cond
+
+    def denoise_decode(self, cond: Optional[torch.Tensor], noise: torch.Tensor, want_latent=False, want_logits=False):
+        """cond [B,256,hc,wc] (or None right after build_condition), noise [B,16,h,w] -> depth [B,1,2h,2w]
+        (+ latent [B,16,h,w], logits)."""
         B, (h, w) = self.batch, self.latent_hw
-        self._check_in(cond, (B, 256, *self.cond_hw))
+        if cond is not None:
+            self._check_in(cond, (B, 256, *self.cond_hw))
         self._check_in(noise, (B, 16, h, w))
         depth = torch.empty(B, 1, 2 * h, 2 * w, device=self.device, dtype=torch.float32)
         latent = torch.empty(B, 16, h, w, device=self.device, dtype=torch.float32) if want_latent else None
         logits = torch.empty_like(depth) if want_logits else None
         ws = self._workspace()
         _cabi.check(self.lib.dd_denoise_decode(
-            self._h, C.c_void_p(cond.data_ptr()), C.c_void_p(noise.data_ptr()),
+            self._h, C.c_void_p(cond.data_ptr() if cond is not None else 0), C.c_void_p(noise.data_ptr()),
             C.c_void_p(latent.data_ptr() if want_latent else 0), C.c_void_p(logits.data_ptr() if want_logits else 0),
             C.c_void_p(depth.data_ptr()), C.c_void_p(self._aligned(ws)), ws.numel() - 1024, C.c_void_p(self._stream())))
         return depth, latent, logits

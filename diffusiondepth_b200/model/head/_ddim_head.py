@@ -93,6 +93,8 @@ class DDIMHeadBase(nn.Module):
         self.use_cuda_graph = True
         self.check_range = True
         self.capture_logits = False      # tests: also keep the decoder's pre-sigmoid z of the last forward
+        self.native_producers = True     # neck + FPN on the engine's tensor-core conv path when the pyramid allows
+        self.capture_cond = False        # tests: keep the NCHW condition map of the last forward
         self.noise_generator: Optional[torch.Generator] = None
         self._engines: Dict[Tuple, DenoiseEngine] = {}
         self._packed_sig = {}
@@ -106,15 +108,36 @@ class DDIMHeadBase(nn.Module):
             sd[k] = getattr(obj, leaf)
         return sd
 
-    def _engine(self, batch, latent_hw, cond_hw, device) -> DenoiseEngine:
+    def _producer_tensors(self):
+        sd = {}
+        for k, v in self.state_dict(keep_vars=True).items():
+            if k.startswith(("hahineck.", "conv_lateral.", "conv_up.")):
+                sd[k] = v
+        return sd
+
+    @staticmethod
+    def _pyramid_ok(feats):
+        """Native FPN needs an exact 2x pyramid (adaptive_avg_pool2d == identity) and 32-multiple channels."""
+        for a, b in zip(feats[:-1], feats[1:]):
+            if a.shape[-2] != 2 * b.shape[-2] or a.shape[-1] != 2 * b.shape[-1]:
+                return False
+        return all(f.shape[1] % 32 == 0 for f in feats)
+
+    def _engine(self, batch, latent_hw, cond_hw, device, feats=None) -> DenoiseEngine:
+        native = feats is not None
         key = (batch, tuple(latent_hw), tuple(cond_hw), str(device), self.diffusion_inference_steps,
-               self.use_cuda_graph)
+               self.use_cuda_graph, native)
         eng = self._engines.get(key)
         tensors = self._engine_tensors()
+        if native:
+            tensors.update(self._producer_tensors())
         sig = tuple((t.data_ptr(), t._version) for t in tensors.values())
         if eng is None:
             eng = DenoiseEngine(self.variant, batch, latent_hw, cond_hw, self.diffusion_inference_steps, device,
                                 cuda_graph=self.use_cuda_graph, check_range=False)
+            if native:
+                eng.enable_producers([f.shape[1] for f in feats], [tuple(f.shape[-2:]) for f in feats],
+                                     has_neck=self.variant == "swin")
             ts, cx, ce = self.scheduler.fused_coefficients(self.diffusion_inference_steps)
             eng.set_schedule(ts, cx, ce)
             self._engines[key] = eng
@@ -158,15 +181,23 @@ class DDIMHeadBase(nn.Module):
         if self.detach_fp is not False and self.detach_fp is not None:
             idx = self.detach_fp if isinstance(self.detach_fp, (list, tuple, range)) else range(len(fp))
             fp = [f.detach() if i in idx else f for i, f in enumerate(fp)]
+        fp = [f.contiguous().float() for f in fp]
+        native = self.native_producers and fp[0].is_cuda and self._pyramid_ok(fp)
         with torch.no_grad(), exact_fp32():
             gt_map_t = self.depth_transform.t(gt_depth_map)
-            cond = self._condition(self._neck(fp)).contiguous()
-        B = cond.shape[0]
+            cond = None if native else self._condition(self._neck(fp)).contiguous()
+        B, dev = fp[0].shape[0], fp[0].device
         latent_hw = tuple(gt_map_t.shape[-2:])
-        x_T = self._draw_noise((B, *gt_map_t.shape[-3:]), cond.device, cond.dtype, noise)
-        eng = self._engine(B, latent_hw, tuple(cond.shape[-2:]), cond.device)
-        refined_depth, refined_depth_t, logits = eng.denoise_decode(cond, x_T, want_latent=True,
-                                                                    want_logits=self.capture_logits)
+        x_T = self._draw_noise((B, *gt_map_t.shape[-3:]), dev, fp[0].dtype, noise)
+        if native:  # neck + FPN + loop + decoder all inside the engine; the condition map never leaves NHWC
+            eng = self._engine(B, latent_hw, tuple(fp[0].shape[-2:]), dev, feats=fp)
+            cond = eng.build_condition(fp, want_cond=self.capture_cond or self.training or self.eval_ddim_loss)
+            refined_depth, refined_depth_t, logits = eng.denoise_decode(None, x_T, want_latent=True,
+                                                                        want_logits=self.capture_logits)
+        else:
+            eng = self._engine(B, latent_hw, tuple(cond.shape[-2:]), dev)
+            refined_depth, refined_depth_t, logits = eng.denoise_decode(cond, x_T, want_latent=True,
+                                                                        want_logits=self.capture_logits)
         self.last_latent, self.last_logits, self.last_cond = refined_depth_t, logits, cond
         if self.check_range:
             eng.poll_status()  # syncs; raises if an activation left the fp16 split range (DESIGN.md "Numerics")

@@ -105,10 +105,31 @@ int dd_finalize_weights(dd_handle h, void* cuda_stream);
  * coefficients; n must equal num_inference_steps. */
 int dd_set_schedule(dd_handle h, const int64_t* timesteps, const double* c_x, const double* c_eps, int32_t n);
 
+/* Optional: also run the step-invariant condition producers natively — HAHI neck (attention gates off, as
+ * the shipped heads configure it: src/model/necks/hahi.py:165-276) and the FPN (head :112-122) — on the same
+ * 3-pass tensor-core path.  Call before dd_finalize_weights; additionally register the reference keys
+ * `hahineck.*` (only if has_neck), `conv_lateral.*`, `conv_up.*`.  Needs an exact 2x feature pyramid (the
+ * FPN's adaptive_avg_pool2d is then the identity) and channel counts that are multiples of 32. */
+typedef struct dd_producer_config {
+  int32_t num_levels;   /* 2..4 */
+  int32_t channels[4];  /* backbone feature channels, finest level first */
+  int32_t heights[4];
+  int32_t widths[4];
+  int32_t has_neck;     /* 1: Swin/MPViT heads (HAHIHeteroNeck in front of the FPN), 0: Res heads */
+} dd_producer_config;
+int dd_enable_producers(dd_handle h, const dd_producer_config* pc);
+
+/* feats[i]: device fp32 NCHW [B, channels[i], heights[i], widths[i]] (the backbone's outputs).  Builds the
+ * 256-channel condition map inside the workspace; a following dd_denoise_decode(cond = NULL, ...) consumes it.
+ * cond_out (nullable): also write it as NCHW [B,256,cond_h,cond_w]. */
+int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, void* workspace,
+                       size_t workspace_bytes, void* cuda_stream);
+
 size_t dd_workspace_bytes(dd_handle h);
 
 /* cond [B,256,cond_h,cond_w], noise [B,16,h,w] -> latent_out [B,16,h,w] (nullable),
- * logit_out [B,1,2h,2w] (nullable; the decoder's pre-sigmoid z), depth_out [B,1,2h,2w]. */
+ * logit_out [B,1,2h,2w] (nullable; the decoder's pre-sigmoid z), depth_out [B,1,2h,2w].
+ * cond may be NULL right after dd_build_condition. */
 int dd_denoise_decode(dd_handle h, const float* cond, const float* noise, float* latent_out, float* logit_out,
                       float* depth_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
 

@@ -130,6 +130,55 @@ def test_loop_and_decode_vs_oracle(variant, hw, T):
     assert torch.equal(outs["graph"], outs["eager"])
 
 
+# ------------------------------------------------------------------------------------------------ producers
+@pytest.mark.parametrize("variant,hw0", [("swin", (16, 32)), ("swin", (24, 40)), ("res", (32, 48))])
+def test_native_neck_and_fpn_vs_oracle(variant, hw0):
+    """dd_build_condition (HAHI neck + FPN on the tensor-core conv path, BN folded, concat-free) vs the fp64
+    restatement of reference necks/hahi.py:165-276 + head :112-122, and vs the mirror's torch-op producers."""
+    head = (_res_head if variant == "res" else _swin_head)(2).to(DEV)
+    with torch.no_grad():  # make BN non-trivial
+        for m in head.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    sd = _head_sd(head)
+    chans = (192, 384, 768, 1536) if variant == "swin" else (64, 128, 256, 512)
+    g = torch.Generator().manual_seed(11)
+    feats = [torch.randn(2, c, hw0[0] >> i, hw0[1] >> i, generator=g) for i, c in enumerate(chans)]
+    fd = [f.to(DEV) for f in feats]
+    lat = (2 * hw0[0], 2 * hw0[1]) if variant == "swin" else hw0
+    eng = head._engine(2, lat, hw0, DEV, feats=fd)
+    cond = eng.build_condition(fd, want_cond=True)
+    eng.poll_status()
+    f64 = [f.double() for f in feats]
+    ref = restate.fpn_condition(sd, restate.hahi_neck(sd, f64) if variant == "swin" else f64)
+    err = (cond.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 5e-5, err
+    from diffusiondepth_b200.model._blocks import exact_fp32
+    with torch.no_grad(), exact_fp32():  # with cuDNN's default TF32 the torch path itself is off by ~5e-3 here
+        torch_cond = head._condition(head._neck(fd))
+    assert (cond - torch_cond).abs().max().item() < 1e-4 * ref.abs().max().item()
+    # the loop consumes the internally built condition: same result as passing it explicitly
+    noise = torch.randn(2, 16, *lat, generator=g).to(DEV)
+    eng.set_schedule(*head.scheduler.fused_coefficients(2))
+    a = eng.denoise_decode(None, noise, want_logits=True)[2]
+    b = head._engine(2, lat, hw0, DEV).denoise_decode(cond, noise, want_logits=True)[2]
+    assert torch.equal(a, b)
+    with pytest.raises(dd.EngineError):
+        eng.denoise_decode(None, noise)  # the built condition is consumed once
+
+
+def test_native_producers_refuse_resampling_pyramids():
+    head = _res_head(2).to(DEV)
+    eng = dd.DenoiseEngine("res", 1, (29, 38), (29, 38), 2, DEV)
+    with pytest.raises(dd.EngineError, match="DD_ERR_UNSUPPORTED"):
+        eng.enable_producers([64, 128, 256, 512], [(29, 38), (15, 19), (8, 10), (4, 5)], has_neck=False)
+    fp = [torch.randn(1, c, h, w, device=DEV) for c, (h, w) in zip((64, 128, 256, 512), ((29, 38), (15, 19), (8, 10), (4, 5)))]
+    assert not head._pyramid_ok(fp)  # the head then keeps the FPN on torch ops (adaptive pooling resamples)
+
+
 # ------------------------------------------------------------------------------------------------ whole plugin
 def _run_plugin(case, batch=None):
     g = helpers.load_golden(case)
@@ -141,6 +190,7 @@ def _run_plugin(case, batch=None):
     sample["noise"] = restate.synthetic_noise(B, g["H"], g["W"], configs.SEED_NOISE)
     sample = {k: v.to(DEV) for k, v in sample.items()}
     m.depth_head.capture_logits = True
+    m.depth_head.capture_cond = True
     with torch.no_grad():
         out = m(sample)
     return g, m, out
