@@ -23,6 +23,11 @@ class DDProducerConfig(C.Structure):
                 ("widths", C.c_int32 * 4), ("has_neck", C.c_int32)]
 
 
+class DDBackboneConfig(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("embed_dims", C.c_int32), ("depths", C.c_int32 * 4),
+                ("num_heads", C.c_int32 * 4), ("window", C.c_int32), ("height", C.c_int32), ("width", C.c_int32)]
+
+
 ABI_VERSION = 1
 VARIANT_RES, VARIANT_SWIN = 0, 1
 FLAG_CUDA_GRAPH, FLAG_SIMT_CONV, FLAG_CHECK_RANGE = 1, 2, 4
@@ -40,6 +45,8 @@ SIGNATURES = {
                                   C.POINTER(C.c_double), C.c_int32]),
     "dd_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "dd_enable_producers": (C.c_int, [C.c_void_p, C.POINTER(DDProducerConfig)]),
+    "dd_enable_backbone": (C.c_int, [C.c_void_p, C.POINTER(DDBackboneConfig)]),
+    "dd_run_backbone": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dd_build_condition": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t,
                                      C.c_void_p]),
     "dd_denoise_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -20,7 +20,8 @@ struct GenConvArgs {
   int cout;           // total output channels (n_tiles * NT)
   const float* shift; // [cout] bias / folded BN shift
   float acc_scale;
-  int relu;
+  int relu;           // activation: 0 none, 1 ReLU, 2 exact (erf) GELU
+  int m_valid;        // > 0: GEMM mode (B = 1, W = 16): only "pixels" (tokens) with index < m_valid are stored
   int shuffle;        // 1: ConvTranspose2d(k=2,s=2): channel n = q*(cout/4)+c goes to pixel (2y+q/2, 2x+q%2), channel c
   float* y32;         // optional fp32 NHWC output
   const float* add32; // optional fp32 NHWC addend (indexed like y32), added after the ReLU
@@ -167,7 +168,7 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
       const int nt = work % p.n_tiles, mt = work / p.n_tiles;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
       const int x = tx * TILE_W + c, y = ty * TILE_H + r;
-      const bool valid = (x < p.W) && (y < p.H);
+      const bool valid = (x < p.W) && (y < p.H) && (p.m_valid <= 0 || (y * p.W + x) < p.m_valid);
       mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
       full_phase ^= (1u << buf);
       tc_fence_after();
@@ -189,7 +190,9 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float t = fmaf(__uint_as_float(rr[j]), p.acc_scale, __ldg(p.shift + n0 + j));
-          v[j] = p.relu ? fmaxf(t, 0.f) : t;
+          if (p.relu == 1) t = fmaxf(t, 0.f);
+          else if (p.relu == 2) t = 0.5f * t * (1.f + erff(t * 0.70710678118654752f));
+          v[j] = t;
         }
         if (p.add32) {
           const float4* a4 = reinterpret_cast<const float4*>(p.add32 + o);

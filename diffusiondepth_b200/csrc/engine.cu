@@ -15,6 +15,7 @@
 #include "../../include/dd_engine.h"
 #include "kernels.cuh"
 #include "convgen.cuh"
+#include "swin.cuh"
 
 namespace {
 
@@ -171,6 +172,34 @@ struct Planes {
   __half* hi = nullptr;
   __half* lo = nullptr;
 };
+struct Gemm {  // Linear layer on the tensor-core GEMM path: W [N][K] as fp16 hi/lo planes
+  int K = 0, N = 0, nt = 256;
+  __half* w_hi = nullptr;
+  __half* w_lo = nullptr;
+  float* bias = nullptr;  // [N] (zeros if the layer has none)
+  float wscale = 1.f;
+  CUtensorMap mb_hi, mb_lo;
+};
+struct SwinBlockW {
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *table = nullptr;
+  Gemm qkv, proj, ffn1, ffn2;
+};
+struct SwinStageW {
+  std::vector<SwinBlockW> blocks;
+  float *out_g = nullptr, *out_b = nullptr, *dn_g = nullptr, *dn_b = nullptr;
+  Gemm reduction;
+};
+struct Backbone {
+  bool enabled = false, ready = false;
+  int E = 0, window = 7, H = 0, W = 0;
+  int depths[4] = {0, 0, 0, 0}, heads[4] = {0, 0, 0, 0}, Hs[4] = {0, 0, 0, 0}, Ws[4] = {0, 0, 0, 0};
+  float *pe_w = nullptr, *pe_b = nullptr, *pe_g = nullptr, *pe_beta = nullptr;
+  SwinStageW stage[4];
+  // workspace views
+  float* X[2] = {nullptr, nullptr};
+  float* QKV = nullptr;
+  Planes AP, HP;
+};
 struct Producers {
   bool enabled = false, ready = false, neck = false;
   int nlev = 0;
@@ -208,6 +237,8 @@ struct dd_engine {
   int* status = nullptr;
   // graph
   Producers prod;
+  Backbone bb;
+  bool feats_ready = false;  // dd_run_backbone has filled the neck's input planes
   bool cond_ready = false;  // dd_build_condition has filled `cond` for the next dd_denoise_decode(cond = NULL)
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
@@ -291,6 +322,19 @@ size_t carve(dd_engine* e, void* base) {
       pv->X[i] = (i == 0) ? v->cond : c.take<float>(px * 256);
       if (i < pc.nlev - 1) pv->UP[i] = c.take<float>(px * 256);
     }
+  }
+  if (e->bb.enabled) {
+    const Backbone& bc = e->bb;
+    Backbone* bv = &v->bb;
+    const size_t m0 = (static_cast<size_t>(g.B) * bc.Hs[0] * bc.Ws[0] + 127) / 128 * 128 + 128;  // padded token count
+    const size_t c0 = bc.E;
+    bv->X[0] = c.take<float>(m0 * c0);
+    bv->X[1] = c.take<float>(m0 * c0);
+    bv->QKV = c.take<float>(m0 * c0 * 3);
+    bv->AP.hi = c.take<__half>(m0 * c0);
+    bv->AP.lo = c.take<__half>(m0 * c0);
+    bv->HP.hi = c.take<__half>(m0 * c0 * 4);
+    bv->HP.lo = c.take<__half>(m0 * c0 * 4);
   }
   return align_up(c.off, 1024);
 }
@@ -670,6 +714,7 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   a.shift = L.shift;
   a.acc_scale = 1.f / (kProdScale * L.wscale);
   a.relu = L.relu;
+  a.m_valid = 0;
   a.shuffle = L.shuffle;
   a.y32 = y32;
   a.add32 = add32;
@@ -698,6 +743,213 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   e->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("convgen launch: ") + cudaGetErrorString(err));
+  return DD_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ Swin backbone
+constexpr float kTokScale = 16.f;  // fp16-split pre-scale of token activations (LayerNorm / GELU / attention outputs)
+
+int copy_param(dd_engine* e, const std::string& key, size_t n, float** out, cudaStream_t st) {
+  const Raw* r = find(e, key);
+  if (!r) return fail(DD_ERR_INVALID, "missing weights: " + key);
+  size_t have = 1;
+  for (int64_t d : r->shape) have *= static_cast<size_t>(d);
+  if (have != n) return fail(DD_ERR_INVALID, "weight shape mismatch: " + key);
+  int rc;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(out), n * 4))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(*out, r->ptr, n * 4, cudaMemcpyDeviceToDevice, st));
+  return DD_OK;
+}
+
+int pack_gemm(dd_engine* e, Gemm& G, const std::string& wkey, const std::string& bkey, int N, int K, cudaStream_t st,
+              float* scratch) {
+  const Raw* w = find(e, wkey);
+  if (!w) return fail(DD_ERR_INVALID, "missing weights: " + wkey);
+  if (w->shape != std::vector<int64_t>{N, K}) return fail(DD_ERR_INVALID, "weight shape mismatch: " + wkey);
+  G.K = K;
+  G.N = N;
+  G.nt = (N % 256 == 0) ? 256 : 192;
+  if (N % G.nt != 0 || K % 32 != 0) return fail(DD_ERR_UNSUPPORTED, "linear layer not tileable: " + wkey);
+  const size_t n = static_cast<size_t>(N) * K;
+  int rc;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&G.w_hi), n * 2))) return rc;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&G.w_lo), n * 2))) return rc;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&G.bias), N * 4))) return rc;
+  if (!bkey.empty()) {
+    const Raw* b = find(e, bkey);
+    if (!b) return fail(DD_ERR_INVALID, "missing weights: " + bkey);
+    CUDA_TRY(cudaMemcpyAsync(G.bias, b->ptr, N * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(G.bias, 0, N * 4, st));
+  }
+  dd::absmax_kernel<<<1, 256, 0, st>>>(w->ptr, static_cast<int>(n), scratch);
+  float amax = 0.f;
+  CUDA_TRY(cudaMemcpyAsync(&amax, scratch, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  G.wscale = (amax > 0.f && isfinite(amax)) ? exp2f(floorf(log2f(32768.f / amax)) - 1.f) : 1.f;
+  dd::pack_gen_weight_kernel<<<256, 256, 0, st>>>(w->ptr, nullptr, G.w_hi, G.w_lo, N, K, 1, 0, G.wscale);
+  CUDA_TRY(cudaGetLastError());
+  if ((rc = make_wgen_map(&G.mb_hi, G.w_hi, N, K, 1, G.nt))) return rc;
+  if ((rc = make_wgen_map(&G.mb_lo, G.w_lo, N, K, 1, G.nt))) return rc;
+  return DD_OK;
+}
+
+int pack_backbone(dd_engine* e, cudaStream_t st, float* scratch) {
+  Backbone& b = e->bb;
+  const std::string P = "backbone.";
+  int rc;
+  if ((rc = copy_param(e, P + "patch_embed.projection.weight", static_cast<size_t>(b.E) * 48, &b.pe_w, st))) return rc;
+  if ((rc = copy_param(e, P + "patch_embed.projection.bias", b.E, &b.pe_b, st))) return rc;
+  if ((rc = copy_param(e, P + "patch_embed.norm.weight", b.E, &b.pe_g, st))) return rc;
+  if ((rc = copy_param(e, P + "patch_embed.norm.bias", b.E, &b.pe_beta, st))) return rc;
+  for (int s = 0; s < 4; ++s) {
+    const int C = b.E << s;
+    SwinStageW& S = b.stage[s];
+    S.blocks.assign(b.depths[s], SwinBlockW());
+    for (int k = 0; k < b.depths[s]; ++k) {
+      SwinBlockW& W = S.blocks[k];
+      const std::string bp = P + "stages." + std::to_string(s) + ".blocks." + std::to_string(k) + ".";
+      if ((rc = copy_param(e, bp + "norm1.weight", C, &W.ln1_g, st))) return rc;
+      if ((rc = copy_param(e, bp + "norm1.bias", C, &W.ln1_b, st))) return rc;
+      if ((rc = copy_param(e, bp + "norm2.weight", C, &W.ln2_g, st))) return rc;
+      if ((rc = copy_param(e, bp + "norm2.bias", C, &W.ln2_b, st))) return rc;
+      if ((rc = copy_param(e, bp + "attn.w_msa.relative_position_bias_table", static_cast<size_t>(169) * b.heads[s], &W.table, st))) return rc;
+      if ((rc = pack_gemm(e, W.qkv, bp + "attn.w_msa.qkv.weight", bp + "attn.w_msa.qkv.bias", 3 * C, C, st, scratch))) return rc;
+      if ((rc = pack_gemm(e, W.proj, bp + "attn.w_msa.proj.weight", bp + "attn.w_msa.proj.bias", C, C, st, scratch))) return rc;
+      if ((rc = pack_gemm(e, W.ffn1, bp + "ffn.layers.0.0.weight", bp + "ffn.layers.0.0.bias", 4 * C, C, st, scratch))) return rc;
+      if ((rc = pack_gemm(e, W.ffn2, bp + "ffn.layers.1.weight", bp + "ffn.layers.1.bias", C, 4 * C, st, scratch))) return rc;
+    }
+    const std::string np = P + "norm" + std::to_string(s) + ".";
+    if ((rc = copy_param(e, np + "weight", C, &S.out_g, st))) return rc;
+    if ((rc = copy_param(e, np + "bias", C, &S.out_b, st))) return rc;
+    if (s < 3) {
+      const std::string dp = P + "stages." + std::to_string(s) + ".downsample.";
+      if ((rc = copy_param(e, dp + "norm.weight", 4 * C, &S.dn_g, st))) return rc;
+      if ((rc = copy_param(e, dp + "norm.bias", 4 * C, &S.dn_b, st))) return rc;
+      if ((rc = pack_gemm(e, S.reduction, dp + "reduction.weight", "", 2 * C, 4 * C, st, scratch))) return rc;
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  b.ready = true;
+  return DD_OK;
+}
+
+// y = act(A[M][K] @ W^T + bias) (+ add32): tokens are laid out as a [ceil(M/16)][16] "image" for the conv kernel
+int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float* y32, const float* add32,
+             const Planes* out, cudaStream_t st) {
+  dd::GenConvArgs a;
+  a.B = 1;
+  a.W = 16;
+  a.H = (M + 15) / 16;
+  a.tiles_x = 1;
+  a.tiles_y = (a.H + dd::TILE_H - 1) / dd::TILE_H;
+  a.m_tiles = a.tiles_y;
+  a.n_tiles = G.N / G.nt;
+  a.kc0 = G.K / 32;
+  a.kc1 = 0;
+  a.taps = 1;
+  a.cout = G.N;
+  a.shift = G.bias;
+  a.acc_scale = 1.f / (kTokScale * G.wscale);
+  a.relu = act;
+  a.m_valid = M;
+  a.shuffle = 0;
+  a.y32 = y32;
+  a.add32 = add32;
+  a.out_hi = out ? out->hi : nullptr;
+  a.out_lo = out ? out->lo : nullptr;
+  a.split_scale = kTokScale;
+  a.status = e->status;
+  CUtensorMap mh, ml;
+  int rc;
+  if ((rc = make_act_map(&mh, A.hi, 1, a.H, 16, G.K, 32))) return rc;
+  if ((rc = make_act_map(&ml, A.lo, 1, a.H, 16, G.K, 32))) return rc;
+  const int work = a.m_tiles * a.n_tiles;
+  const int grid = work < e->sm_count ? work : e->sm_count;
+  if (G.nt == 256)
+    dd::convgen_umma_kernel<256><<<grid, 256, dd::GenCfg<256>::SMEM_BYTES, st>>>(mh, ml, mh, ml, G.mb_hi, G.mb_lo, a);
+  else
+    dd::convgen_umma_kernel<192><<<grid, 256, dd::GenCfg<192>::SMEM_BYTES, st>>>(mh, ml, mh, ml, G.mb_hi, G.mb_lo, a);
+  e->launches++;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(err));
+  return DD_OK;
+}
+
+int run_ln(dd_engine* e, int C, const float* x, const float* g, const float* b, const Planes& out, int M, float* nchw,
+           int HW, cudaStream_t st) {
+  const int grid = (M + 7) / 8;
+  switch (C) {
+    case 192: dd::ln_split_kernel<192><<<grid, 256, 0, st>>>(x, g, b, out.hi, out.lo, kTokScale, M, nchw, HW, e->status); break;
+    case 384: dd::ln_split_kernel<384><<<grid, 256, 0, st>>>(x, g, b, out.hi, out.lo, kTokScale, M, nchw, HW, e->status); break;
+    case 768: dd::ln_split_kernel<768><<<grid, 256, 0, st>>>(x, g, b, out.hi, out.lo, kTokScale, M, nchw, HW, e->status); break;
+    case 1536: dd::ln_split_kernel<1536><<<grid, 256, 0, st>>>(x, g, b, out.hi, out.lo, kTokScale, M, nchw, HW, e->status); break;
+    default: return fail(DD_ERR_UNSUPPORTED, "LayerNorm width not instantiated");
+  }
+  e->launches++;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("ln_split: ") + cudaGetErrorString(err));
+  return DD_OK;
+}
+
+int run_swin(dd_engine* e, const float* rgb, float* const* feats_out, cudaStream_t st) {
+  Backbone& b = e->bb;
+  const int B = e->cfg.batch;
+  {
+    const int M0 = B * b.Hs[0] * b.Ws[0];
+    dd::patch_embed_kernel<192><<<(M0 + 7) / 8, 192, 0, st>>>(rgb, b.pe_w, b.pe_b, b.pe_g, b.pe_beta, b.X[0], B, b.H, b.W,
+                                                               b.Hs[0], b.Ws[0]);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  int rc;
+  for (int s = 0; s < 4; ++s) {
+    const int C = b.E << s, H = b.Hs[s], W = b.Ws[s], M = B * H * W, nH = b.heads[s];
+    float* x = b.X[s & 1];
+    const int ws = b.window;
+    const int Hp = (H + ws - 1) / ws * ws, Wp = (W + ws - 1) / ws * ws;
+    for (int k = 0; k < b.depths[s]; ++k) {
+      const SwinBlockW& Wt = b.stage[s].blocks[k];
+      if ((rc = run_ln(e, C, x, Wt.ln1_g, Wt.ln1_b, b.AP, M, nullptr, 0, st))) return rc;
+      if ((rc = run_gemm(e, Wt.qkv, b.AP, M, 0, b.QKV, nullptr, nullptr, st))) return rc;
+      dd::AttnArgs aa;
+      aa.qkv = b.QKV;
+      aa.qkv_bias = Wt.qkv.bias;
+      aa.bias_table = Wt.table;
+      aa.out_hi = b.AP.hi;
+      aa.out_lo = b.AP.lo;
+      aa.scale_out = kTokScale;
+      aa.B = B; aa.H = H; aa.W = W; aa.C = C; aa.nH = nH;
+      aa.shift = (k & 1) ? ws / 2 : 0;
+      aa.Hp = Hp; aa.Wp = Wp; aa.nWx = Wp / ws; aa.nWy = Hp / ws;
+      aa.status = e->status;
+      dd::window_attention_kernel<<<B * aa.nWx * aa.nWy * nH, 64, 0, st>>>(aa);
+      e->launches++;
+      CUDA_TRY(cudaGetLastError());
+      if ((rc = run_gemm(e, Wt.proj, b.AP, M, 0, x, x, nullptr, st))) return rc;      // x += proj(attn)
+      if ((rc = run_ln(e, C, x, Wt.ln2_g, Wt.ln2_b, b.AP, M, nullptr, 0, st))) return rc;
+      if ((rc = run_gemm(e, Wt.ffn1, b.AP, M, 2, nullptr, nullptr, &b.HP, st))) return rc;  // GELU(fc1) -> planes
+      if ((rc = run_gemm(e, Wt.ffn2, b.HP, M, 0, x, x, nullptr, st))) return rc;      // x += fc2(...)
+    }
+    // per-stage output norm straight into the neck's input planes (+ NCHW copy on request)
+    if ((rc = run_ln(e, C, x, b.stage[s].out_g, b.stage[s].out_b, e->prod.F[s], M, feats_out ? feats_out[s] : nullptr,
+                     H * W, st))) return rc;
+    if (s < 3) {
+      const int M2 = B * b.Hs[s + 1] * b.Ws[s + 1];
+      const int grid = (M2 + 7) / 8;
+      const SwinStageW& S = b.stage[s];
+      switch (C) {
+        case 192: dd::merge_ln_split_kernel<192><<<grid, 256, 0, st>>>(x, S.dn_g, S.dn_b, b.AP.hi, b.AP.lo, kTokScale, B, H, W, e->status); break;
+        case 384: dd::merge_ln_split_kernel<384><<<grid, 256, 0, st>>>(x, S.dn_g, S.dn_b, b.AP.hi, b.AP.lo, kTokScale, B, H, W, e->status); break;
+        case 768: dd::merge_ln_split_kernel<768><<<grid, 256, 0, st>>>(x, S.dn_g, S.dn_b, b.AP.hi, b.AP.lo, kTokScale, B, H, W, e->status); break;
+        default: return fail(DD_ERR_UNSUPPORTED, "patch merging width not instantiated");
+      }
+      e->launches++;
+      CUDA_TRY(cudaGetLastError());
+      if ((rc = run_gemm(e, S.reduction, b.AP, M2, 0, b.X[(s + 1) & 1], nullptr, nullptr, st))) return rc;
+    }
+  }
   return DD_OK;
 }
 
@@ -768,7 +1020,8 @@ static const char* kKeys[] = {
 int dd_set_weight(dd_handle h, const char* name, const float* dev_ptr, const int64_t* shape, int32_t ndim) {
   if (!h || !name || !dev_ptr || ndim < 0 || ndim > 4) return fail(DD_ERR_INVALID, "bad argument");
   bool known = strncmp(name, "hahineck.", 9) == 0 || strncmp(name, "conv_lateral.", 13) == 0 ||
-               strncmp(name, "conv_up.", 8) == 0;  // step-invariant producers (optional, dd_enable_producers)
+               strncmp(name, "conv_up.", 8) == 0 ||  // step-invariant producers (optional, dd_enable_producers)
+               strncmp(name, "backbone.", 9) == 0;    // native Swin backbone (optional, dd_enable_backbone)
   for (const char* k : kKeys) known |= (strcmp(k, name) == 0);
   if (!known) return fail(DD_ERR_INVALID, std::string("unknown weight key: ") + name);
   Raw r;
@@ -862,6 +1115,9 @@ int dd_finalize_weights(dd_handle h, void* cuda_stream) {
   h->prod.ready = false;
   if (h->prod.enabled)
     if ((rc = pack_producers(h, st, scratch))) return rc;
+  h->bb.ready = false;
+  if (h->bb.enabled)
+    if ((rc = pack_backbone(h, st, scratch))) return rc;
   h->weights_ready = true;
   return DD_OK;
 }
@@ -1020,7 +1276,8 @@ int dd_enable_producers(dd_handle h, const dd_producer_config* pc) {
 
 int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, void* workspace, size_t workspace_bytes,
                        void* cuda_stream) {
-  if (!h || !feats) return fail(DD_ERR_INVALID, "null argument");
+  if (!h) return fail(DD_ERR_INVALID, "null argument");
+  if (!feats && !h->feats_ready) return fail(DD_ERR_INVALID, "feats is NULL but dd_run_backbone has not run");
   if (!h->prod.enabled || !h->weights_ready || !h->prod.ready)
     return fail(DD_ERR_INVALID, "producers not enabled / weights not finalized");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
@@ -1029,9 +1286,12 @@ int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, 
   if ((rc = bind_workspace(h, workspace, workspace_bytes))) return rc;
   Producers& p = h->prod;
   const int B = h->cfg.batch;
-  CUDA_TRY(cudaMemsetAsync(h->status, 0, 64, st));
-  h->launches = 0;
-  for (int i = 0; i < p.nlev; ++i) {
+  if (feats) {
+    CUDA_TRY(cudaMemsetAsync(h->status, 0, 64, st));
+    h->launches = 0;
+  }  // else: dd_run_backbone already wrote the input planes F[i] (and owns the status / launch counters)
+  h->feats_ready = false;
+  for (int i = 0; feats && i < p.nlev; ++i) {
     if (!feats[i]) return fail(DD_ERR_INVALID, "null feature map");
     const int P = p.H[i] * p.W[i];
     dim3 grid((P + 31) / 32, (p.C[i] + 31) / 32, B), block(32, 8);
@@ -1067,6 +1327,52 @@ int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, 
     if ((rc = transpose_out(h->cond, cond_out, B, 256, p.H[0] * p.W[0], st))) return rc;
     h->launches++;
   }
+  return DD_OK;
+}
+
+int dd_enable_backbone(dd_handle h, const dd_backbone_config* bc) {
+  if (!h || !bc) return fail(DD_ERR_INVALID, "null argument");
+  if (bc->kind != DD_BACKBONE_SWIN) return fail(DD_ERR_UNSUPPORTED, "only the Swin backbone runs natively");
+  if (!h->prod.enabled || !h->prod.neck || h->prod.nlev != 4)
+    return fail(DD_ERR_INVALID, "dd_enable_producers (4 levels, has_neck) must be called first");
+  if (bc->embed_dims != 192 || bc->window != 7)
+    return fail(DD_ERR_UNSUPPORTED, "native Swin is instantiated for embed_dims 192 (Swin-L), window 7");
+  Backbone b;
+  b.enabled = true;
+  b.E = bc->embed_dims;
+  b.window = bc->window;
+  b.H = bc->height;
+  b.W = bc->width;
+  int hh = (bc->height + 3) / 4, ww = (bc->width + 3) / 4;
+  for (int s = 0; s < 4; ++s) {
+    b.depths[s] = bc->depths[s];
+    b.heads[s] = bc->num_heads[s];
+    if (b.depths[s] < 1 || (b.E << s) != 32 * b.heads[s]) return fail(DD_ERR_UNSUPPORTED, "Swin head_dim must be 32");
+    b.Hs[s] = hh;
+    b.Ws[s] = ww;
+    if (hh != h->prod.H[s] || ww != h->prod.W[s] || (b.E << s) != h->prod.C[s])
+      return fail(DD_ERR_INVALID, "backbone stage geometry does not match the producer pyramid");
+    hh = (hh + 1) / 2;
+    ww = (ww + 1) / 2;
+  }
+  h->bb = b;
+  h->weights_ready = false;
+  h->ws = nullptr;
+  return DD_OK;
+}
+
+int dd_run_backbone(dd_handle h, const float* rgb, float* const* feats_out, void* workspace, size_t workspace_bytes,
+                    void* cuda_stream) {
+  if (!h || !rgb) return fail(DD_ERR_INVALID, "null argument");
+  if (!h->bb.enabled || !h->weights_ready || !h->bb.ready) return fail(DD_ERR_INVALID, "backbone not enabled / weights not finalized");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc;
+  if ((rc = bind_workspace(h, workspace, workspace_bytes))) return rc;
+  CUDA_TRY(cudaMemsetAsync(h->status, 0, 64, st));
+  h->launches = 0;
+  if ((rc = run_swin(h, rgb, feats_out, st))) return rc;
+  h->feats_ready = true;
   return DD_OK;
 }
 

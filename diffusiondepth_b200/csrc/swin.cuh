@@ -1,0 +1,289 @@
+// Swin Transformer pieces that are not GEMMs (the GEMMs run on convgen_umma_kernel in "GEMM mode"):
+// patch embedding (4x4/s4 conv + LayerNorm), LayerNorm -> fp16 hi/lo planes, 2x2 patch-merge gather + LayerNorm,
+// 7x7 (shifted-)window attention with relative-position bias and the reference's finite -100 shift mask,
+// per-stage output LayerNorm written straight into the neck's input planes.
+// Token stream layout: x fp32 [B*H*W][C] (NHWC flattened), qkv fp32 [M][3C] with the reference's [3][nH][32]
+// column interleave.  Restates reference src/model/backbone/swin.py (PatchMerging :64-88, WindowMSA :150-189,
+// ShiftWindowMSA :250-325, SwinBlock :426-437, SwinTransformer.forward :756-777) and
+// backbone/utils.py:282-302 (PatchEmbedSwin); parity traps: SURVEY.md Appendix C.
+#pragma once
+#include "kernels.cuh"
+
+namespace dd {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ LayerNorm(C) -> scaled fp16 hi/lo planes
+// one warp per token; C = 32 * VPT elements (VPT <= 48).  Optionally also writes fp32 NCHW (stage outputs).
+template <int C>
+__global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, __half* __restrict__ hi,
+                                                       __half* __restrict__ lo, float scale, int M, float* nchw_out,
+                                                       int HW, int* status) {
+  constexpr int VPT = C / 32;
+  const int token = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (token >= M) return;
+  const float* row = x + static_cast<size_t>(token) * C;
+  float v[VPT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    v[i] = row[lane + 32 * i];
+    s += v[i];
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const float d = v[i] - mean;
+    s2 = fmaf(d, d, s2);
+  }
+  const float rstd = rsqrtf(warp_sum(s2) * (1.f / C) + 1e-5f);
+  bool ov = false;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + 32 * i;
+    const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    __half h, l;
+    split_f16(y, scale, h, l, ov);
+    hi[static_cast<size_t>(token) * C + c] = h;
+    lo[static_cast<size_t>(token) * C + c] = l;
+    if (nchw_out) {
+      const int b = token / HW, p = token - b * HW;
+      nchw_out[(static_cast<size_t>(b) * C + c) * HW + p] = y;
+    }
+  }
+  if (ov) atomicOr(status, 1);
+}
+
+// ------------------------------------------------------------------ patch embed: conv 4x4 s4 (3 -> E) + bias + LayerNorm(E)
+// rgb fp32 NCHW [B,3,H,W] (zero right/bottom pad to a multiple of 4) -> x fp32 [B*Hp*Wp][E]; one block of E threads
+// per token group.
+template <int E>
+__global__ void __launch_bounds__(E) patch_embed_kernel(const float* __restrict__ rgb, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ x, int B, int H,
+                                                        int W, int Hp, int Wp) {
+  constexpr int TOK = 8;  // tokens per block
+  __shared__ float patch[TOK][48];
+  __shared__ float red[2][TOK][E / 32];
+  const int t0 = blockIdx.x * TOK;
+  const int M = B * Hp * Wp;
+  for (int i = threadIdx.x; i < TOK * 48; i += E) {
+    const int tk = i / 48, k = i % 48;  // k = c*16 + ky*4 + kx (Conv2d weight order [E][3][4][4])
+    const int token = t0 + tk;
+    float v = 0.f;
+    if (token < M) {
+      const int b = token / (Hp * Wp), r = token % (Hp * Wp), py = r / Wp, px = r % Wp;
+      const int c = k / 16, ky = (k % 16) / 4, kx = k % 4;
+      const int yy = py * 4 + ky, xx = px * 4 + kx;
+      if (yy < H && xx < W) v = rgb[((static_cast<size_t>(b) * 3 + c) * H + yy) * W + xx];
+    }
+    patch[tk][k] = v;
+  }
+  __syncthreads();
+  const int e = threadIdx.x;
+  float wr[48];
+#pragma unroll
+  for (int k = 0; k < 48; ++k) wr[k] = w[e * 48 + k];
+  float acc[TOK];
+#pragma unroll
+  for (int tk = 0; tk < TOK; ++tk) {
+    float a = bias[e];
+#pragma unroll
+    for (int k = 0; k < 48; ++k) a = fmaf(patch[tk][k], wr[k], a);
+    acc[tk] = a;
+  }
+  const int warp = e >> 5, lane = e & 31;
+#pragma unroll
+  for (int tk = 0; tk < TOK; ++tk) {
+    const float s = warp_sum(acc[tk]);
+    if (lane == 0) red[0][tk][warp] = s;
+  }
+  __syncthreads();
+  float mean[TOK];
+#pragma unroll
+  for (int tk = 0; tk < TOK; ++tk) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < E / 32; ++wv) s += red[0][tk][wv];
+    mean[tk] = s * (1.f / E);
+    const float d = acc[tk] - mean[tk];
+    const float s2 = warp_sum(d * d);
+    if (lane == 0) red[1][tk][warp] = s2;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int tk = 0; tk < TOK; ++tk) {
+    float s2 = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < E / 32; ++wv) s2 += red[1][tk][wv];
+    const float rstd = rsqrtf(s2 * (1.f / E) + 1e-5f);
+    const int token = t0 + tk;
+    if (token < M) x[static_cast<size_t>(token) * E + e] = (acc[tk] - mean[tk]) * rstd * gamma[e] + beta[e];
+  }
+}
+
+// ------------------------------------------------------------------ patch merging gather + LayerNorm(4C) -> planes
+// x [B,H,W,C] -> tokens [B,(H+1)/2,(W+1)/2,4C] with feature index c*4 + ky*2 + kx (nn.Unfold order), zero pad
+// for odd H/W, then LayerNorm over 4C.  One warp per output token.
+template <int C>
+__global__ void __launch_bounds__(256) merge_ln_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, __half* __restrict__ hi,
+                                                             __half* __restrict__ lo, float scale, int B, int H, int W,
+                                                             int* status) {
+  constexpr int F = 4 * C, VPT = F / 32;
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const int M2 = B * H2 * W2;
+  const int token = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (token >= M2) return;
+  const int b = token / (H2 * W2), r = token % (H2 * W2), oy = r / W2, ox = r % W2;
+  float v[VPT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int f = lane + 32 * i;
+    const int c = f >> 2, ky = (f >> 1) & 1, kx = f & 1;
+    const int yy = 2 * oy + ky, xx = 2 * ox + kx;
+    v[i] = (yy < H && xx < W) ? x[((static_cast<size_t>(b) * H + yy) * W + xx) * C + c] : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) * (1.f / F);
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const float d = v[i] - mean;
+    s2 = fmaf(d, d, s2);
+  }
+  const float rstd = rsqrtf(warp_sum(s2) * (1.f / F) + 1e-5f);
+  bool ov = false;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int f = lane + 32 * i;
+    const float y = (v[i] - mean) * rstd * gamma[f] + beta[f];
+    __half h, l;
+    split_f16(y, scale, h, l, ov);
+    hi[static_cast<size_t>(token) * F + f] = h;
+    lo[static_cast<size_t>(token) * F + f] = l;
+  }
+  if (ov) atomicOr(status, 1);
+}
+
+// ------------------------------------------------------------------ (shifted) 7x7 window attention, head_dim 32
+// One block (64 threads) per (window, head).  The reference pads the *normalised* tokens with zeros before the
+// qkv Linear, so a padded token carries q/k/v = the qkv bias; it attends and is attended to (only the shift mask,
+// built from 3x3 region ids on the padded map, hides anything).  Output: attention result scattered back to the
+// un-rolled, un-padded token positions as fp16 hi/lo planes [M][C] (input of the proj GEMM).
+struct AttnArgs {
+  const float* qkv;        // [M][3C]
+  const float* qkv_bias;   // [3C]
+  const float* bias_table; // [169][nH]
+  __half* out_hi;
+  __half* out_lo;
+  float scale_out;
+  int B, H, W, C, nH, shift;
+  int Hp, Wp, nWx, nWy;
+  int* status;
+};
+__global__ void __launch_bounds__(64) window_attention_kernel(const AttnArgs a) {
+  constexpr int WS = 7, N = 49, D = 32;
+  __shared__ float sq[N][D + 1], sk[N][D + 1], sv[N][D + 1];
+  __shared__ float sp[N][N + 1];  // attention scores / probabilities, one row per query thread
+  __shared__ int s_tok[N];   // source token index or -1 for padding
+  __shared__ int s_reg[N];   // shift-mask region id
+  const int head = blockIdx.x % a.nH;
+  const int win = blockIdx.x / a.nH;
+  const int wx = win % a.nWx, wy = (win / a.nWx) % a.nWy, b = win / (a.nWx * a.nWy);
+  const int tid = threadIdx.x;
+  if (tid < N) {
+    const int iy = tid / WS, ix = tid % WS;
+    const int sy = wy * WS + iy, sx = wx * WS + ix;  // coordinates in the rolled, padded frame
+    int reg = 0;
+    if (a.shift > 0) {
+      const int ry = sy < a.Hp - WS ? 0 : (sy < a.Hp - a.shift ? 1 : 2);
+      const int rx = sx < a.Wp - WS ? 0 : (sx < a.Wp - a.shift ? 1 : 2);
+      reg = ry * 3 + rx;
+    }
+    const int py = (sy + a.shift) % a.Hp, px = (sx + a.shift) % a.Wp;  // torch.roll(x, -shift)[i] = x[(i+shift) % n]
+    s_tok[tid] = (py < a.H && px < a.W) ? (b * a.H + py) * a.W + px : -1;
+    s_reg[tid] = reg;
+  }
+  __syncthreads();
+  const float qscale = rsqrtf(static_cast<float>(D));  // head_dim ** -0.5, applied to q before q @ k^T
+  for (int i = tid; i < N * D; i += 64) {
+    const int t = i / D, d = i % D;
+    const int tok = s_tok[t];
+    const int col = head * D + d;
+    float q, k, v;
+    if (tok >= 0) {
+      const float* row = a.qkv + static_cast<size_t>(tok) * 3 * a.C;
+      q = row[col];
+      k = row[a.C + col];
+      v = row[2 * a.C + col];
+    } else {
+      q = a.qkv_bias[col];
+      k = a.qkv_bias[a.C + col];
+      v = a.qkv_bias[2 * a.C + col];
+    }
+    sq[t][d] = q * qscale;
+    sk[t][d] = k;
+    sv[t][d] = v;
+  }
+  __syncthreads();
+  if (tid >= N) return;
+  const int i = tid;
+  const int iy = i / WS, ix = i % WS;
+  float* p = sp[i];
+  float mx = -INFINITY;
+#pragma unroll 7
+  for (int j = 0; j < N; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) s = fmaf(sq[i][d], sk[j][d], s);
+    const int jy = j / WS, jx = j % WS;
+    const int rel = (iy - jy + WS - 1) * (2 * WS - 1) + (ix - jx + WS - 1);
+    s += a.bias_table[rel * a.nH + head];
+    if (a.shift > 0 && s_reg[i] != s_reg[j]) s += -100.0f;
+    p[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.f;
+#pragma unroll 7
+  for (int j = 0; j < N; ++j) {
+    p[j] = expf(p[j] - mx);
+    sum += p[j];
+  }
+  const float inv = 1.f / sum;
+  float o[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = 0.f;
+#pragma unroll 7
+  for (int j = 0; j < N; ++j) {
+    const float pj = p[j] * inv;
+#pragma unroll
+    for (int d = 0; d < D; ++d) o[d] = fmaf(pj, sv[j][d], o[d]);
+  }
+  const int tok = s_tok[i];
+  if (tok < 0) return;  // padded query rows are cropped by the reference (:319-320)
+  bool ov = false;
+  __align__(16) __half hh[D];
+  __align__(16) __half ll[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) split_f16(o[d], a.scale_out, hh[d], ll[d], ov);
+  uint4* dh = reinterpret_cast<uint4*>(a.out_hi + static_cast<size_t>(tok) * a.C + head * D);
+  uint4* dl = reinterpret_cast<uint4*>(a.out_lo + static_cast<size_t>(tok) * a.C + head * D);
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    dh[d] = reinterpret_cast<const uint4*>(hh)[d];
+    dl[d] = reinterpret_cast<const uint4*>(ll)[d];
+  }
+  if (ov) atomicOr(a.status, 1);
+}
+
+}  // namespace dd

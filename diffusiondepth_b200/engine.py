@@ -72,10 +72,13 @@ class DenoiseEngine:
         self._ws: Optional[torch.Tensor] = None
         self._keep = []  # fp32 contiguous copies handed to dd_set_weight must outlive finalize
         self.producers = None
+        self.backbone = None
 
     # ---------------------------------------------------------------- setup
     def load_weights(self, tensors: Dict[str, torch.Tensor]):
         keys = DENOISER_KEYS + DECODER_KEYS + (FUSE_KEYS if self.variant == "swin" else ())
+        if self.backbone is not None:
+            keys = keys + tuple(k for k in tensors if k.startswith("backbone.") and tensors[k].is_floating_point())
         if self.producers is not None:
             keys = keys + tuple(k for k in tensors if k.startswith(("hahineck.", "conv_lateral.", "conv_up."))
                                 and not k.endswith("num_batches_tracked") and tensors[k].dim() <= 4
@@ -103,6 +106,17 @@ class DenoiseEngine:
         self.producers = (tuple(channels), tuple(tuple(s_) for s_ in sizes), bool(has_neck))
         self._ws = None
 
+    def enable_backbone(self, image_hw, embed_dims=192, depths=(2, 2, 18, 2), num_heads=(6, 12, 24, 48), window=7):
+        """Run the Swin backbone natively as well (after enable_producers, before load_weights)."""
+        bc = _cabi.DDBackboneConfig()
+        bc.kind, bc.embed_dims, bc.window = 1, int(embed_dims), int(window)
+        bc.height, bc.width = int(image_hw[0]), int(image_hw[1])
+        for i in range(4):
+            bc.depths[i], bc.num_heads[i] = int(depths[i]), int(num_heads[i])
+        _cabi.check(self.lib.dd_enable_backbone(self._h, C.byref(bc)))
+        self.backbone = (tuple(image_hw), int(embed_dims))
+        self._ws = None
+
     def set_schedule(self, timesteps, c_x, c_eps):
         n = len(timesteps)
         _cabi.check(self.lib.dd_set_schedule(self._h, (C.c_int64 * n)(*[int(t) for t in timesteps]),
@@ -127,15 +141,31 @@ class DenoiseEngine:
             raise EngineError(f"expected contiguous fp32 {tuple(shape)} on {self.device}, got {tuple(t.shape)} "
                               f"{t.dtype} {t.device}")
 
+    def run_backbone(self, rgb: torch.Tensor, want_feats=False):
+        """rgb [B,3,H,W] -> the four Swin stage outputs, left inside the workspace for `build_condition(None)`;
+        `want_feats` also returns them as fp32 NCHW tensors."""
+        if self.backbone is None:
+            raise EngineError("enable_backbone() was not called")
+        self._check_in(rgb, (self.batch, 3, *self.backbone[0]))
+        chans, sizes, _ = self.producers
+        feats = [torch.empty(self.batch, c, *hw, device=self.device) for c, hw in zip(chans, sizes)] if want_feats else None
+        ptrs = (C.c_void_p * 4)(*[f.data_ptr() for f in feats]) if want_feats else None
+        ws = self._workspace()
+        _cabi.check(self.lib.dd_run_backbone(self._h, C.c_void_p(rgb.data_ptr()), ptrs, C.c_void_p(self._aligned(ws)),
+                                             ws.numel() - 1024, C.c_void_p(self._stream())))
+        return feats
+
     def build_condition(self, feats, want_cond=False):
         """Backbone feature maps (fp32 NCHW, finest first) -> condition map, natively (neck + FPN).  The result
         stays inside the workspace for the next `denoise_decode(None, noise)`; `want_cond` also returns it."""
         if self.producers is None:
             raise EngineError("enable_producers() was not called")
         chans, sizes, _ = self.producers
-        for f, c, hw in zip(feats, chans, sizes):
-            self._check_in(f, (self.batch, c, *hw))
-        ptrs = (C.c_void_p * 4)(*([f.data_ptr() for f in feats] + [0] * (4 - len(feats))))
+        ptrs = None
+        if feats is not None:
+            for f, c, hw in zip(feats, chans, sizes):
+                self._check_in(f, (self.batch, c, *hw))
+            ptrs = (C.c_void_p * 4)(*([f.data_ptr() for f in feats] + [0] * (4 - len(feats))))
         cond = torch.empty(self.batch, 256, *self.cond_hw, device=self.device) if want_cond else None
         ws = self._workspace()
         _cabi.check(self.lib.dd_build_condition(self._h, ptrs, C.c_void_p(cond.data_ptr() if want_cond else 0),

@@ -30,6 +30,8 @@ class Diffusion_DCbase_Model(nn.Module):
                 init_cfg=args))
         self.depth_head = depth_head
         self.depth_keys = depth_keys
+        if hasattr(self.depth_head, "attach_backbone"):
+            self.depth_head.attach_backbone(self.depth_backbone)
 
     def extract_depth(self, img, depth_map, depth_mask, gt_depth_map, return_loss=False, img_metas=None,
                       weight_map=None, instance_masks=None, **kwargs):
@@ -38,8 +40,12 @@ class Diffusion_DCbase_Model(nn.Module):
         if gt_depth_map is not None:
             gt_depth_map = gt_depth_map.view(B, 1, *depth_map.shape[-2:])
         depth_mask = depth_mask.view(*depth_map.shape)
-        with torch.no_grad(), exact_fp32():
-            fp = self.depth_backbone(img)
+        head = self.depth_head
+        if hasattr(head, "can_run_backbone") and head.can_run_backbone(self.depth_backbone, img):
+            fp = None  # the engine runs the Swin backbone itself (DenoiseEngine.run_backbone)
+        else:
+            with torch.no_grad(), exact_fp32():
+                fp = self.depth_backbone(img)
         return self.depth_head(fp, depth_map, depth_mask, gt_depth_map=gt_depth_map, return_loss=return_loss,
                                weight_map=weight_map, instance_masks=instance_masks, image=img, **kwargs)
 

@@ -94,6 +94,8 @@ class DDIMHeadBase(nn.Module):
         self.check_range = True
         self.capture_logits = False      # tests: also keep the decoder's pre-sigmoid z of the last forward
         self.native_producers = True     # neck + FPN on the engine's tensor-core conv path when the pyramid allows
+        self.native_backbone = True      # Swin-L backbone on the engine's GEMM/attention path (needs native_producers)
+        self.__dict__['_backbone_ref'] = None  # weakref to the model's depth_backbone (set by Diffusion_DCbase_Model)
         self.capture_cond = False        # tests: keep the NCHW condition map of the last forward
         self.noise_generator: Optional[torch.Generator] = None
         self._engines: Dict[Tuple, DenoiseEngine] = {}
@@ -123,21 +125,57 @@ class DDIMHeadBase(nn.Module):
                 return False
         return all(f.shape[1] % 32 == 0 for f in feats)
 
-    def _engine(self, batch, latent_hw, cond_hw, device, feats=None) -> DenoiseEngine:
+    def attach_backbone(self, backbone):
+        self.__dict__['_backbone_ref'] = weakref.ref(backbone)
+
+    def _backbone(self):
+        return self._backbone_ref() if self._backbone_ref is not None else None
+
+    @staticmethod
+    def swin_pyramid(image_hw):
+        """Stage output sizes of a patch-4 Swin for an (H, W) image, finest first."""
+        h, w = (image_hw[0] + 3) // 4, (image_hw[1] + 3) // 4
+        sizes = []
+        for _ in range(4):
+            sizes.append((h, w))
+            h, w = (h + 1) // 2, (w + 1) // 2
+        return sizes
+
+    def can_run_backbone(self, backbone, img) -> bool:
+        """Native Swin-L path: CUDA input, Swin-L architecture, exact 2x stage pyramid (needed by the native FPN)."""
+        if not (self.native_producers and self.native_backbone and self.variant == "swin" and img.is_cuda):
+            return False
+        if type(backbone).__name__ != "SwinTransformer" or getattr(backbone, "num_features", None) != [192, 384, 768, 1536]:
+            return False
+        if [len(s.blocks) for s in backbone.stages] != [2, 2, 18, 2]:
+            return False
+        sizes = self.swin_pyramid(img.shape[-2:])
+        return all(a[0] == 2 * b[0] and a[1] == 2 * b[1] for a, b in zip(sizes[:-1], sizes[1:]))
+
+    def _engine(self, batch, latent_hw, cond_hw, device, feats=None, image_hw=None) -> DenoiseEngine:
+        """feats: backbone feature maps, or a (channels, sizes) pyramid spec -> native neck/FPN;
+        image_hw: additionally run the Swin backbone natively."""
         native = feats is not None
+        if native and not isinstance(feats, tuple):
+            feats = ([f.shape[1] for f in feats], [tuple(f.shape[-2:]) for f in feats])
         key = (batch, tuple(latent_hw), tuple(cond_hw), str(device), self.diffusion_inference_steps,
-               self.use_cuda_graph, native)
+               self.use_cuda_graph, native, tuple(image_hw) if image_hw is not None else None)
         eng = self._engines.get(key)
         tensors = self._engine_tensors()
         if native:
             tensors.update(self._producer_tensors())
+        if image_hw is not None:
+            for k, v in self._backbone().state_dict(keep_vars=True).items():
+                if v.is_floating_point():
+                    tensors["backbone." + k] = v
         sig = tuple((t.data_ptr(), t._version) for t in tensors.values())
         if eng is None:
             eng = DenoiseEngine(self.variant, batch, latent_hw, cond_hw, self.diffusion_inference_steps, device,
                                 cuda_graph=self.use_cuda_graph, check_range=False)
             if native:
-                eng.enable_producers([f.shape[1] for f in feats], [tuple(f.shape[-2:]) for f in feats],
-                                     has_neck=self.variant == "swin")
+                eng.enable_producers(feats[0], feats[1], has_neck=self.variant == "swin")
+            if image_hw is not None:
+                eng.enable_backbone(image_hw)
             ts, cx, ce = self.scheduler.fused_coefficients(self.diffusion_inference_steps)
             eng.set_schedule(ts, cx, ce)
             self._engines[key] = eng
@@ -177,21 +215,37 @@ class DDIMHeadBase(nn.Module):
         return torch.randn(shape, generator=g, device=device, dtype=dtype)
 
     # ------------------------------------------------------------------------------------------ forward
-    def forward(self, fp, depth_map, depth_mask, gt_depth_map=None, return_loss=False, noise=None, **kwargs):
-        if self.detach_fp is not False and self.detach_fp is not None:
-            idx = self.detach_fp if isinstance(self.detach_fp, (list, tuple, range)) else range(len(fp))
-            fp = [f.detach() if i in idx else f for i, f in enumerate(fp)]
-        fp = [f.contiguous().float() for f in fp]
-        native = self.native_producers and fp[0].is_cuda and self._pyramid_ok(fp)
+    def forward(self, fp, depth_map, depth_mask, gt_depth_map=None, return_loss=False, noise=None, image=None,
+                **kwargs):
+        """fp: backbone feature maps — or None, meaning "run the backbone natively from `image`" (the model
+        wrapper does that when `can_run_backbone` holds)."""
+        with_backbone = fp is None
+        if with_backbone:
+            B, dev, dtype = image.shape[0], image.device, torch.float32
+            sizes = self.swin_pyramid(image.shape[-2:])
+            native = True
+        else:
+            if self.detach_fp is not False and self.detach_fp is not None:
+                idx = self.detach_fp if isinstance(self.detach_fp, (list, tuple, range)) else range(len(fp))
+                fp = [f.detach() if i in idx else f for i, f in enumerate(fp)]
+            fp = [f.contiguous().float() for f in fp]
+            B, dev, dtype = fp[0].shape[0], fp[0].device, fp[0].dtype
+            native = self.native_producers and fp[0].is_cuda and self._pyramid_ok(fp)
         with torch.no_grad(), exact_fp32():
             gt_map_t = self.depth_transform.t(gt_depth_map)
             cond = None if native else self._condition(self._neck(fp)).contiguous()
-        B, dev = fp[0].shape[0], fp[0].device
         latent_hw = tuple(gt_map_t.shape[-2:])
-        x_T = self._draw_noise((B, *gt_map_t.shape[-3:]), dev, fp[0].dtype, noise)
-        if native:  # neck + FPN + loop + decoder all inside the engine; the condition map never leaves NHWC
-            eng = self._engine(B, latent_hw, tuple(fp[0].shape[-2:]), dev, feats=fp)
-            cond = eng.build_condition(fp, want_cond=self.capture_cond or self.training or self.eval_ddim_loss)
+        x_T = self._draw_noise((B, *gt_map_t.shape[-3:]), dev, dtype, noise)
+        if native:  # (backbone +) neck + FPN + loop + decoder inside the engine; the condition map never leaves NHWC
+            want_cond = self.capture_cond or self.training or self.eval_ddim_loss
+            if with_backbone:
+                eng = self._engine(B, latent_hw, sizes[0], dev, feats=(list(self.fpn_in_channels), sizes),
+                                   image_hw=tuple(image.shape[-2:]))
+                eng.run_backbone(image.contiguous().float())
+                cond = eng.build_condition(None, want_cond=want_cond)
+            else:
+                eng = self._engine(B, latent_hw, tuple(fp[0].shape[-2:]), dev, feats=fp)
+                cond = eng.build_condition(fp, want_cond=want_cond)
             refined_depth, refined_depth_t, logits = eng.denoise_decode(None, x_T, want_latent=True,
                                                                         want_logits=self.capture_logits)
         else:

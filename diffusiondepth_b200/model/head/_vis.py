@@ -8,6 +8,9 @@ from .._blocks import exact_fp32
 
 
 class VisMixin:
+    def can_run_backbone(self, backbone, img) -> bool:
+        return False  # the step-wise Vis path takes backbone features from the torch modules
+
     def forward(self, fp, depth_map, depth_mask, gt_depth_map=None, return_loss=False, noise=None, **kwargs):
         with torch.no_grad(), exact_fp32():
             gt_map_t = self.depth_transform.t(gt_depth_map)

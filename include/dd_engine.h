@@ -120,10 +120,33 @@ typedef struct dd_producer_config {
 int dd_enable_producers(dd_handle h, const dd_producer_config* pc);
 
 /* feats[i]: device fp32 NCHW [B, channels[i], heights[i], widths[i]] (the backbone's outputs).  Builds the
- * 256-channel condition map inside the workspace; a following dd_denoise_decode(cond = NULL, ...) consumes it.
+ * (feats may be NULL right after dd_run_backbone.)  256-channel condition map inside the workspace; a following dd_denoise_decode(cond = NULL, ...) consumes it.
  * cond_out (nullable): also write it as NCHW [B,256,cond_h,cond_w]. */
 int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, void* workspace,
                        size_t workspace_bytes, void* cuda_stream);
+
+/* Optional: also run the Swin backbone natively (reference src/model/backbone/swin.py:756-777): patch embed,
+ * LayerNorms, QKV / proj / FFN / patch-merging Linears on the 3-pass tensor-core GEMM path, 7x7 (shifted-)window
+ * attention with relative-position bias and the finite -100 mask, per-stage output norms written straight into the
+ * neck's input planes.  Requires dd_enable_producers(4 levels, has_neck = 1) with matching geometry; register the
+ * reference keys of `depth_backbone.*` as "backbone.<key>" (the int64 `relative_position_index` buffers are not
+ * needed).  Instantiated for Swin-L (embed_dims 192, head_dim 32, window 7). */
+enum dd_backbone_kind { DD_BACKBONE_SWIN = 1 };
+typedef struct dd_backbone_config {
+  int32_t kind;        /* enum dd_backbone_kind */
+  int32_t embed_dims;  /* 192 */
+  int32_t depths[4];   /* 2, 2, 18, 2 */
+  int32_t num_heads[4];/* 6, 12, 24, 48 */
+  int32_t window;      /* 7 */
+  int32_t height, width; /* input image size */
+} dd_backbone_config;
+int dd_enable_backbone(dd_handle h, const dd_backbone_config* bc);
+
+/* rgb: device fp32 NCHW [B,3,height,width].  Leaves the four stage outputs in the workspace for a following
+ * dd_build_condition(feats = NULL, ...); feats_out (nullable array of 4 nullable pointers) also receives them as
+ * fp32 NCHW [B, C_s, H_s, W_s]. */
+int dd_run_backbone(dd_handle h, const float* rgb, float* const* feats_out, void* workspace, size_t workspace_bytes,
+                    void* cuda_stream);
 
 size_t dd_workspace_bytes(dd_handle h);
 
