@@ -46,7 +46,7 @@ struct GenCfg {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_constant__ CUtensorMap tmA0_lo,
                     const __grid_constant__ CUtensorMap tmA1_hi, const __grid_constant__ CUtensorMap tmA1_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -77,7 +77,7 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);
+      mbar_init(&tempty_bar[b], 8);  // eight epilogue warps
     }
     fence_barrier_init();
   }
@@ -157,35 +157,57 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
       buf ^= 1;
     }
   } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue: 8 warps = 2 groups x 128 TMEM lanes;
+    // group g drains the 32-column chunks with index % 2 == g, and prefetches its next addend chunk while the
+    // current one is processed (short-K GEMMs are otherwise bound by this loop's global-load latency).
     const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
     const int m = q * 32 + lane;
     const int r = m >> 4, c = m & 15;
     uint32_t full_phase = 0;
     int buf = 0;
     bool overflow = false;
     const int cq = p.cout >> 2;
+    constexpr int NCH = NT / 32;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
       const int nt = work % p.n_tiles, mt = work / p.n_tiles;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
       const int x = tx * TILE_W + c, y = ty * TILE_H + r;
       const bool valid = (x < p.W) && (y < p.H) && (p.m_valid <= 0 || (y * p.W + x) < p.m_valid);
+      auto offset_of = [&](int n0) -> size_t {
+        if (p.shuffle) {
+          const int sub = n0 / cq, cc = n0 - sub * cq;
+          return ((static_cast<size_t>(img) * (2 * p.H) + (2 * y + (sub >> 1))) * (2 * p.W) + (2 * x + (sub & 1))) * cq + cc;
+        }
+        return ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout + n0;
+      };
+      float4 ad_next[8];
+      const bool has_add = (p.add32 != nullptr) && valid;
+      if (has_add && grp < NCH) {
+        const float4* a4 = reinterpret_cast<const float4*>(p.add32 + offset_of(nt * NT + grp * 32));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ad_next[j] = a4[j];
+      }
       mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
       full_phase ^= (1u << buf);
       tc_fence_after();
-#pragma unroll 1
-      for (int ch0 = 0; ch0 < NT; ch0 += 32) {
+#pragma unroll
+      for (int ci = grp; ci < NCH; ci += 2) {
+        const int ch0 = ci * 32;
+        float4 ad[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ad[j] = ad_next[j];
+        if (has_add && ci + 2 < NCH) {
+          const float4* a4 = reinterpret_cast<const float4*>(p.add32 + offset_of(nt * NT + ch0 + 64));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ad_next[j] = a4[j];
+        }
         uint32_t rr[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * NT + ch0), rr);
         tmem_ld_wait();
         if (!valid) continue;
         const int n0 = nt * NT + ch0;
-        size_t o;  // element offset of channel n0's destination
-        if (p.shuffle) {
-          const int sub = n0 / cq, cc = n0 - sub * cq;
-          o = ((static_cast<size_t>(img) * (2 * p.H) + (2 * y + (sub >> 1))) * (2 * p.W) + (2 * x + (sub & 1))) * cq + cc;
-        } else {
-          o = ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout + n0;
-        }
+        const size_t o = offset_of(n0);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -195,14 +217,12 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           v[j] = t;
         }
         if (p.add32) {
-          const float4* a4 = reinterpret_cast<const float4*>(p.add32 + o);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 t = a4[j];
-            v[4 * j] += t.x;
-            v[4 * j + 1] += t.y;
-            v[4 * j + 2] += t.z;
-            v[4 * j + 3] += t.w;
+            v[4 * j] += ad[j].x;
+            v[4 * j + 1] += ad[j].y;
+            v[4 * j + 2] += ad[j].z;
+            v[4 * j + 3] += ad[j].w;
           }
         }
         if (p.y32) {
@@ -215,10 +235,10 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           __align__(16) __half lo[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float s = v[j] * p.split_scale;
-            overflow |= (fabsf(s) > 60000.f);
-            hi[j] = __float2half_rn(s);
-            lo[j] = __float2half_rn(s - __half2float(hi[j]));
+            const float sc = v[j] * p.split_scale;
+            overflow |= (fabsf(sc) > 60000.f);
+            hi[j] = __float2half_rn(sc);
+            lo[j] = __float2half_rn(sc - __half2float(hi[j]));
           }
           uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
           uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);

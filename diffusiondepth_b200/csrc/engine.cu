@@ -441,9 +441,15 @@ int run_apply(dd_engine* e, int which, const float* temb, int temb_bstride, __ha
   a.out_lo = out_lo;
   a.scale = kActScale;
   a.status = e->status;
-  constexpr int PPB = 256 / (C / 8);
-  dim3 grid((g.P + PPB - 1) / PPB, g.B);
-  dd::gn_apply_split_kernel<C, COND><<<grid, 256, 0, st>>>(a);
+  // the tiled bilinear kernel needs the 32-pixel segment's source span to fit its 18-column staging buffer
+  if (COND == 2 && C == 256 && a.rx * 31.f + 2.f <= 18.f) {
+    dim3 grid((g.w + 31) / 32, g.h, g.B);
+    dd::gn_apply_up_split_kernel<<<grid, 256, 0, st>>>(a);
+  } else {
+    constexpr int PPB = 256 / (C / 8);
+    dim3 grid((g.P + PPB - 1) / PPB, g.B);
+    dd::gn_apply_split_kernel<C, COND><<<grid, 256, 0, st>>>(a);
+  }
   e->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("gn_apply: ") + cudaGetErrorString(err));
@@ -737,9 +743,9 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   const int work = a.m_tiles * a.n_tiles;
   const int grid = work < e->sm_count ? work : e->sm_count;
   if (L.nt == 256)
-    dd::convgen_umma_kernel<256><<<grid, 256, dd::GenCfg<256>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
+    dd::convgen_umma_kernel<256><<<grid, 384, dd::GenCfg<256>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
   else
-    dd::convgen_umma_kernel<192><<<grid, 256, dd::GenCfg<192>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
+    dd::convgen_umma_kernel<192><<<grid, 384, dd::GenCfg<192>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
   e->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("convgen launch: ") + cudaGetErrorString(err));
@@ -868,9 +874,9 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   const int work = a.m_tiles * a.n_tiles;
   const int grid = work < e->sm_count ? work : e->sm_count;
   if (G.nt == 256)
-    dd::convgen_umma_kernel<256><<<grid, 256, dd::GenCfg<256>::SMEM_BYTES, st>>>(mh, ml, mh, ml, G.mb_hi, G.mb_lo, a);
+    dd::convgen_umma_kernel<256><<<grid, 384, dd::GenCfg<256>::SMEM_BYTES, st>>>(mh, ml, mh, ml, G.mb_hi, G.mb_lo, a);
   else
-    dd::convgen_umma_kernel<192><<<grid, 256, dd::GenCfg<192>::SMEM_BYTES, st>>>(mh, ml, mh, ml, G.mb_hi, G.mb_lo, a);
+    dd::convgen_umma_kernel<192><<<grid, 384, dd::GenCfg<192>::SMEM_BYTES, st>>>(mh, ml, mh, ml, G.mb_hi, G.mb_lo, a);
   e->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(err));

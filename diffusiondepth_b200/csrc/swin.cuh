@@ -193,10 +193,11 @@ struct AttnArgs {
 };
 __global__ void __launch_bounds__(64) window_attention_kernel(const AttnArgs a) {
   constexpr int WS = 7, N = 49, D = 32;
-  __shared__ float sq[N][D + 1], sk[N][D + 1], sv[N][D + 1];
-  __shared__ float sp[N][N + 1];  // attention scores / probabilities, one row per query thread
-  __shared__ int s_tok[N];   // source token index or -1 for padding
-  __shared__ int s_reg[N];   // shift-mask region id
+  __shared__ __align__(16) float sk[N][D];   // read as broadcast float4 rows
+  __shared__ __align__(16) float sv[N][D];
+  __shared__ float sp[N][N + 1];             // scores / probabilities, one row per query thread
+  __shared__ int s_tok[N];                   // source token index or -1 for padding
+  __shared__ int s_reg[N];                   // shift-mask region id
   const int head = blockIdx.x % a.nH;
   const int win = blockIdx.x / a.nH;
   const int wx = win % a.nWx, wy = (win / a.nWx) % a.nWy, b = win / (a.nWx * a.nWy);
@@ -215,59 +216,75 @@ __global__ void __launch_bounds__(64) window_attention_kernel(const AttnArgs a) 
     s_reg[tid] = reg;
   }
   __syncthreads();
-  const float qscale = rsqrtf(static_cast<float>(D));  // head_dim ** -0.5, applied to q before q @ k^T
-  for (int i = tid; i < N * D; i += 64) {
-    const int t = i / D, d = i % D;
+  // k, v rows -> shared (8 lanes x float4 per row)
+  for (int i = tid; i < N * (D / 4); i += 64) {
+    const int t = i / (D / 4), d4 = i % (D / 4);
     const int tok = s_tok[t];
-    const int col = head * D + d;
-    float q, k, v;
-    if (tok >= 0) {
-      const float* row = a.qkv + static_cast<size_t>(tok) * 3 * a.C;
-      q = row[col];
-      k = row[a.C + col];
-      v = row[2 * a.C + col];
-    } else {
-      q = a.qkv_bias[col];
-      k = a.qkv_bias[a.C + col];
-      v = a.qkv_bias[2 * a.C + col];
+    const int col = head * D + d4 * 4;
+    const float* base = tok >= 0 ? a.qkv + static_cast<size_t>(tok) * 3 * a.C : a.qkv_bias;
+    *reinterpret_cast<float4*>(&sk[t][d4 * 4]) = *reinterpret_cast<const float4*>(base + a.C + col);
+    *reinterpret_cast<float4*>(&sv[t][d4 * 4]) = *reinterpret_cast<const float4*>(base + 2 * a.C + col);
+  }
+  // own query row -> registers, pre-scaled by head_dim ** -0.5 (applied to q before q @ k^T, swin.py:163)
+  const int i = tid < N ? tid : N - 1;
+  float q[D];
+  {
+    const int tok = s_tok[i];
+    const float* base = (tok >= 0 ? a.qkv + static_cast<size_t>(tok) * 3 * a.C : a.qkv_bias) + head * D;
+    const float qscale = rsqrtf(static_cast<float>(D));
+#pragma unroll
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      const float4 t = *reinterpret_cast<const float4*>(base + d4 * 4);
+      q[4 * d4] = t.x * qscale;
+      q[4 * d4 + 1] = t.y * qscale;
+      q[4 * d4 + 2] = t.z * qscale;
+      q[4 * d4 + 3] = t.w * qscale;
     }
-    sq[t][d] = q * qscale;
-    sk[t][d] = k;
-    sv[t][d] = v;
   }
   __syncthreads();
   if (tid >= N) return;
-  const int i = tid;
   const int iy = i / WS, ix = i % WS;
+  const int my_reg = s_reg[i];
   float* p = sp[i];
   float mx = -INFINITY;
-#pragma unroll 7
   for (int j = 0; j < N; ++j) {
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int d = 0; d < D; ++d) s = fmaf(sq[i][d], sk[j][d], s);
-    const int jy = j / WS, jx = j % WS;
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      const float4 kk = *reinterpret_cast<const float4*>(&sk[j][d4 * 4]);
+      s0 = fmaf(q[4 * d4], kk.x, s0);
+      s1 = fmaf(q[4 * d4 + 1], kk.y, s1);
+      s2 = fmaf(q[4 * d4 + 2], kk.z, s2);
+      s3 = fmaf(q[4 * d4 + 3], kk.w, s3);
+    }
+    float s = (s0 + s1) + (s2 + s3);
+    const int jy = j / WS, jx = j - jy * WS;
     const int rel = (iy - jy + WS - 1) * (2 * WS - 1) + (ix - jx + WS - 1);
-    s += a.bias_table[rel * a.nH + head];
-    if (a.shift > 0 && s_reg[i] != s_reg[j]) s += -100.0f;
+    s += __ldg(a.bias_table + rel * a.nH + head);
+    if (a.shift > 0 && my_reg != s_reg[j]) s += -100.0f;
     p[j] = s;
     mx = fmaxf(mx, s);
   }
   float sum = 0.f;
-#pragma unroll 7
   for (int j = 0; j < N; ++j) {
-    p[j] = expf(p[j] - mx);
-    sum += p[j];
+    const float e = expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
   }
   const float inv = 1.f / sum;
   float o[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) o[d] = 0.f;
-#pragma unroll 7
   for (int j = 0; j < N; ++j) {
     const float pj = p[j] * inv;
 #pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = fmaf(pj, sv[j][d], o[d]);
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      const float4 vv = *reinterpret_cast<const float4*>(&sv[j][d4 * 4]);
+      o[4 * d4] = fmaf(pj, vv.x, o[4 * d4]);
+      o[4 * d4 + 1] = fmaf(pj, vv.y, o[4 * d4 + 1]);
+      o[4 * d4 + 2] = fmaf(pj, vv.z, o[4 * d4 + 2]);
+      o[4 * d4 + 3] = fmaf(pj, vv.w, o[4 * d4 + 3]);
+    }
   }
   const int tok = s_tok[i];
   if (tok < 0) return;  // padded query rows are cropped by the reference (:319-320)
