@@ -38,9 +38,12 @@ struct GenCfg {
   static constexpr int A_BYTES = TILE_M * ROW_BYTES;  // 8 KB per plane
   static constexpr int B_BYTES = NT * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;  // per-warp 32x32 fp32 transpose tile (XOR-swizzled)
+  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + XPOSE_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   static constexpr int TMEM_COLS = 512;
   static_assert(NT % 32 == 0 && NT <= 256 && 2 * NT <= 512, "bad N tile");
 };
@@ -59,6 +62,7 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* xpose = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,12 +162,15 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue: 8 warps = 2 groups x 128 TMEM lanes;
-    // group g drains the 32-column chunks with index % 2 == g, and prefetches its next addend chunk while the
-    // current one is processed (short-K GEMMs are otherwise bound by this loop's global-load latency).
+    // group g drains the 32-column chunks with index % 2 == g.  tcgen05.ld hands each thread one ROW (pixel/token) of
+    // the chunk; a per-warp XOR-swizzled 32x32 shared-memory tile turns that into one COLUMN per lane, so every global
+    // access below is a fully coalesced 128-byte row segment (row-per-thread stores were the bottleneck of short-K GEMMs:
+    // 32 partial lines per instruction).
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     const int m = q * 32 + lane;
     const int r = m >> 4, c = m & 15;
+    float* T = xpose + (warp - 4) * 1024;
     uint32_t full_phase = 0;
     int buf = 0;
     bool overflow = false;
@@ -174,63 +181,77 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
       const int x = tx * TILE_W + c, y = ty * TILE_H + r;
       const bool valid = (x < p.W) && (y < p.H) && (p.m_valid <= 0 || (y * p.W + x) < p.m_valid);
-      auto offset_of = [&](int n0) -> size_t {
-        if (p.shuffle) {
-          const int sub = n0 / cq, cc = n0 - sub * cq;
-          return ((static_cast<size_t>(img) * (2 * p.H) + (2 * y + (sub >> 1))) * (2 * p.W) + (2 * x + (sub & 1))) * cq + cc;
-        }
-        return ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout + n0;
-      };
-      float4 ad_next[8];
-      const bool has_add = (p.add32 != nullptr) && valid;
-      if (has_add && grp < NCH) {
-        const float4* a4 = reinterpret_cast<const float4*>(p.add32 + offset_of(nt * NT + grp * 32));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ad_next[j] = a4[j];
-      }
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      // element offset of this lane's row at channel 0 (non-shuffle) -- fits 32 bits for every tensor we produce
+      const uint32_t row_base = static_cast<uint32_t>(((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout);
       mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
       full_phase ^= (1u << buf);
       tc_fence_after();
-#pragma unroll
+      const bool xpose_path = (p.out_hi == nullptr);  // fp32-only traffic: coalesce through the transpose tile
       for (int ci = grp; ci < NCH; ci += 2) {
         const int ch0 = ci * 32;
-        float4 ad[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ad[j] = ad_next[j];
-        if (has_add && ci + 2 < NCH) {
-          const float4* a4 = reinterpret_cast<const float4*>(p.add32 + offset_of(nt * NT + ch0 + 64));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ad_next[j] = a4[j];
-        }
+        const int n0 = nt * NT + ch0;
         uint32_t rr[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * NT + ch0), rr);
         tmem_ld_wait();
-        if (!valid) continue;
-        const int n0 = nt * NT + ch0;
-        const size_t o = offset_of(n0);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = fmaf(__uint_as_float(rr[j]), p.acc_scale, __ldg(p.shift + n0 + j));
-          if (p.relu == 1) t = fmaxf(t, 0.f);
-          else if (p.relu == 2) t = 0.5f * t * (1.f + erff(t * 0.70710678118654752f));
-          v[j] = t;
+        uint32_t o_lane;
+        if (p.shuffle) {
+          const int sub = n0 / cq, cc = n0 - sub * cq;
+          o_lane = static_cast<uint32_t>(
+              ((static_cast<size_t>(img) * (2 * p.H) + (2 * y + (sub >> 1))) * (2 * p.W) + (2 * x + (sub & 1))) * cq + cc);
+        } else {
+          o_lane = row_base + static_cast<uint32_t>(n0);
         }
-        if (p.add32) {
+        if (xpose_path) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j] += ad[j].x;
-            v[4 * j + 1] += ad[j].y;
-            v[4 * j + 2] += ad[j].z;
-            v[4 * j + 3] += ad[j].w;
+          for (int j = 0; j < 32; ++j) T[lane * 32 + ((j ^ lane) & 31)] = __uint_as_float(rr[j]);
+          __syncwarp();
+          const float sh = __ldg(p.shift + n0 + lane);
+#pragma unroll
+          for (int r0 = 0; r0 < 32; r0 += 8) {
+            uint32_t o[8];
+            float ad[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {  // issue the (coalesced) addend loads of 8 rows before any store
+              o[k] = __shfl_sync(0xffffffffu, o_lane, r0 + k) + lane;
+              ad[k] = (p.add32 && ((vmask >> (r0 + k)) & 1u)) ? __ldg(p.add32 + o[k]) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (!((vmask >> (r0 + k)) & 1u)) continue;  // warp-uniform
+              float t = fmaf(T[(r0 + k) * 32 + ((lane ^ (r0 + k)) & 31)], p.acc_scale, sh);
+              if (p.relu == 1) t = fmaxf(t, 0.f);
+              else if (p.relu == 2) t = 0.5f * t * (1.f + erff(t * 0.70710678118654752f));
+              if (p.y32) p.y32[o[k]] = t + ad[k];
+            }
           }
-        }
-        if (p.y32) {
-          float4* d4 = reinterpret_cast<float4*>(p.y32 + o);
+          __syncwarp();
+        } else if (valid) {
+          // row-per-thread path (fp16 plane outputs: 64 contiguous bytes per row and plane)
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (p.out_hi) {
+          for (int j = 0; j < 32; ++j) {
+            float t = fmaf(__uint_as_float(rr[j]), p.acc_scale, __ldg(p.shift + n0 + j));
+            if (p.relu == 1) t = fmaxf(t, 0.f);
+            else if (p.relu == 2) t = 0.5f * t * (1.f + erff(t * 0.70710678118654752f));
+            v[j] = t;
+          }
+          if (p.add32) {
+            const float4* a4 = reinterpret_cast<const float4*>(p.add32 + o_lane);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(a4 + j);
+              v[4 * j] += t.x;
+              v[4 * j + 1] += t.y;
+              v[4 * j + 2] += t.z;
+              v[4 * j + 3] += t.w;
+            }
+          }
+          if (p.y32) {
+            float4* d4 = reinterpret_cast<float4*>(p.y32 + o_lane);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
           __align__(16) __half hi[32];
           __align__(16) __half lo[32];
 #pragma unroll
@@ -240,8 +261,8 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
             hi[j] = __float2half_rn(sc);
             lo[j] = __float2half_rn(sc - __half2float(hi[j]));
           }
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o_lane);
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o_lane);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             dh[j] = reinterpret_cast<const uint4*>(hi)[j];

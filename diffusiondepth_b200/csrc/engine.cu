@@ -1382,6 +1382,67 @@ int dd_run_backbone(dd_handle h, const float* rgb, float* const* feats_out, void
   return DD_OK;
 }
 
+// Debug / tuning aid: time the GEMM-mode kernel on synthetic planes.  mode: 0 fp32 out, 1 fp32 out + residual add,
+// 2 GELU -> planes, 3 no output at all (mainloop + TMEM drain only).
+int dd_bench_gemm(dd_handle h, int32_t M, int32_t K, int32_t N, int32_t mode, int32_t iters, float* ms_out) {
+  if (!h || !ms_out || M < 1 || K % 32 || N % 192 && N % 256) return fail(DD_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->cap_stream;
+  const size_t Mp = (static_cast<size_t>(M) + 127) / 128 * 128 + 128;
+  Planes A, O;
+  Gemm G;
+  float *y = nullptr, *bias = nullptr;
+  int* status = nullptr;
+  CUDA_TRY(cudaMalloc(&A.hi, Mp * K * 2));
+  CUDA_TRY(cudaMalloc(&A.lo, Mp * K * 2));
+  CUDA_TRY(cudaMalloc(&O.hi, Mp * N * 2));
+  CUDA_TRY(cudaMalloc(&O.lo, Mp * N * 2));
+  CUDA_TRY(cudaMalloc(&y, Mp * N * 4));
+  CUDA_TRY(cudaMalloc(&G.w_hi, static_cast<size_t>(N) * K * 2));
+  CUDA_TRY(cudaMalloc(&G.w_lo, static_cast<size_t>(N) * K * 2));
+  CUDA_TRY(cudaMalloc(&bias, N * 4));
+  CUDA_TRY(cudaMalloc(&status, 64));
+  CUDA_TRY(cudaMemsetAsync(A.hi, 0x11, Mp * K * 2, st));
+  CUDA_TRY(cudaMemsetAsync(A.lo, 0x01, Mp * K * 2, st));
+  CUDA_TRY(cudaMemsetAsync(G.w_hi, 0x11, static_cast<size_t>(N) * K * 2, st));
+  CUDA_TRY(cudaMemsetAsync(G.w_lo, 0x01, static_cast<size_t>(N) * K * 2, st));
+  CUDA_TRY(cudaMemsetAsync(bias, 0, N * 4, st));
+  CUDA_TRY(cudaMemsetAsync(y, 0, Mp * N * 4, st));
+  G.K = K;
+  G.N = N;
+  G.nt = (N % 256 == 0) ? 256 : 192;
+  G.bias = bias;
+  G.wscale = 1.f;
+  int rc;
+  if ((rc = make_wgen_map(&G.mb_hi, G.w_hi, N, K, 1, G.nt))) return rc;
+  if ((rc = make_wgen_map(&G.mb_lo, G.w_lo, N, K, 1, G.nt))) return rc;
+  int* saved = h->status;
+  h->status = status;
+  auto once = [&]() {
+    return run_gemm(h, G, A, M, mode == 2 ? 2 : 0, (mode == 0 || mode == 1) ? y : nullptr, mode == 1 ? y : nullptr,
+                    mode == 2 ? &O : nullptr, st);
+  };
+  for (int i = 0; i < 3; ++i)
+    if ((rc = once())) return rc;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i)
+    if ((rc = once())) return rc;
+  CUDA_TRY(cudaEventRecord(e1, st));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_out = ms / iters;
+  h->status = saved;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  for (void* p : {(void*)A.hi, (void*)A.lo, (void*)O.hi, (void*)O.lo, (void*)y, (void*)G.w_hi, (void*)G.w_lo, (void*)bias, (void*)status})
+    cudaFree(p);
+  return DD_OK;
+}
+
 int64_t dd_last_launch_count(dd_handle h) { return h ? h->launches : 0; }
 
 int dd_poll_status(dd_handle h, void* cuda_stream) {

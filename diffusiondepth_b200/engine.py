@@ -237,6 +237,11 @@ class DenoiseEngine:
                                            ws.numel() - 1024, C.c_void_p(self._stream())))
         return float(ms.value)
 
+    def bench_gemm(self, M: int, K: int, N: int, mode: int = 0, iters: int = 20) -> float:
+        ms = C.c_float()
+        _cabi.check(self.lib.dd_bench_gemm(self._h, M, K, N, mode, iters, C.byref(ms)))
+        return float(ms.value)
+
     def poll_status(self) -> None:
         """Synchronise the current stream; raises EngineError(DD_ERR_RANGE) if the fp16 split overflowed."""
         _cabi.check(self.lib.dd_poll_status(self._h, C.c_void_p(self._stream())))

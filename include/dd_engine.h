@@ -186,6 +186,10 @@ size_t dd_conv3x3_workspace_bytes(int32_t batch, int32_t cin, int32_t cout, int3
 int dd_bench_conv(dd_handle h, int32_t cin, int32_t cout, int32_t iters, float* ms_out, void* workspace,
                   size_t workspace_bytes, void* cuda_stream);
 
+/* Tuning aid: average milliseconds per launch of the GEMM-mode kernel (tokens [M,K] x weights [N,K]^T) on
+ * synthetic operands.  mode 0: fp32 out, 1: fp32 out + residual add, 2: GELU -> fp16 planes, 3: no output. */
+int dd_bench_gemm(dd_handle h, int32_t M, int32_t K, int32_t N, int32_t mode, int32_t iters, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif
