@@ -56,11 +56,13 @@ struct ConvCfg {
   static constexpr int A_BYTES = TILE_M * ROW_BYTES;  // one plane
   static constexpr int B_BYTES = COUT * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-  static constexpr int SMEM_BUDGET = 200 * 1024;
+  static constexpr int SMEM_BUDGET = 196 * 1024;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static_assert(STAGES >= 2, "stage too large");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + scratch*/;
+  static constexpr int XPOSE_BYTES = 4 * 32 * 32 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (coalesced y stores)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + scratch*/ + XPOSE_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   static constexpr int TMEM_COLS_RAW = 2 * COUT;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : (TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512)));
   static constexpr int CH = COUT < 32 ? COUT : 32;    // epilogue column chunk
@@ -81,6 +83,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [2][4 warps][4 groups][2]  (64 floats)
+  float* xpose = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 512);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -190,6 +193,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const int x = tx * TILE_W + c, y = ty * TILE_H + r;
       const bool valid = (x < p.W) && (y < p.H);
       const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      const uint32_t row_off = static_cast<uint32_t>(pix * COUT);  // < 2^32 elements for every tensor of the path
+      float* T = xpose + q * 1024;
 
       mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
       full_phase ^= (1u << buf);
@@ -232,7 +238,20 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           }
         }
 
-        if (valid) {
+        if constexpr ((EPI == EPI_F32_STATS || EPI == EPI_F32) && C::CH == 32) {
+          // thread = row after tcgen05.ld; go through the XOR-swizzled tile so that lane = column and every store
+          // instruction writes one full 128-byte row segment (row-per-thread stores made the short-K layers
+          // epilogue-bound: 32 partial lines per instruction)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) T[lane * 32 + ((j ^ lane) & 31)] = v[j];
+          __syncwarp();
+#pragma unroll 8
+          for (int rw = 0; rw < 32; ++rw) {
+            const uint32_t o = __shfl_sync(0xffffffffu, row_off, rw) + ch0 + lane;
+            if ((vmask >> rw) & 1u) p.y32[o] = T[rw * 32 + ((lane ^ rw) & 31)];
+          }
+          __syncwarp();
+        } else if (valid) {
           if constexpr (EPI == EPI_F32_STATS || EPI == EPI_F32) {
             float4* dst = reinterpret_cast<float4*>(p.y32 + pix * COUT + ch0);
 #pragma unroll

@@ -178,7 +178,9 @@ struct Gemm {  // Linear layer on the tensor-core GEMM path: W [N][K] as fp16 hi
   __half* w_lo = nullptr;
   float* bias = nullptr;  // [N] (zeros if the layer has none)
   float wscale = 1.f;
-  CUtensorMap mb_hi, mb_lo;
+  CUtensorMap mb_hi, mb_lo;          // box {32, nt}
+  bool alt = false;                  // N tiles by both 256 and 192: second pair of maps for the other width
+  CUtensorMap mb_hi_alt, mb_lo_alt;  // box {32, 192}
 };
 struct SwinBlockW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *table = nullptr;
@@ -798,6 +800,11 @@ int pack_gemm(dd_engine* e, Gemm& G, const std::string& wkey, const std::string&
   CUDA_TRY(cudaGetLastError());
   if ((rc = make_wgen_map(&G.mb_hi, G.w_hi, N, K, 1, G.nt))) return rc;
   if ((rc = make_wgen_map(&G.mb_lo, G.w_lo, N, K, 1, G.nt))) return rc;
+  G.alt = (G.nt == 256 && N % 192 == 0);
+  if (G.alt) {
+    if ((rc = make_wgen_map(&G.mb_hi_alt, G.w_hi, N, K, 1, 192))) return rc;
+    if ((rc = make_wgen_map(&G.mb_lo_alt, G.w_lo, N, K, 1, 192))) return rc;
+  }
   return DD_OK;
 }
 
@@ -851,7 +858,15 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   a.tiles_x = 1;
   a.tiles_y = (a.H + dd::TILE_H - 1) / dd::TILE_H;
   a.m_tiles = a.tiles_y;
-  a.n_tiles = G.N / G.nt;
+  // wave quantisation: with few M tiles (deep Swin stages) pick the N-tile width whose last wave wastes least
+  int nt = G.nt;
+  if (G.alt) {
+    auto cost = [&](int w) { return ((a.m_tiles * (G.N / w) + e->sm_count - 1) / e->sm_count) * w; };
+    if (cost(192) < cost(256)) nt = 192;
+  }
+  const CUtensorMap& mbh = (nt == G.nt) ? G.mb_hi : G.mb_hi_alt;
+  const CUtensorMap& mbl = (nt == G.nt) ? G.mb_lo : G.mb_lo_alt;
+  a.n_tiles = G.N / nt;
   a.kc0 = G.K / 32;
   a.kc1 = 0;
   a.taps = 1;
@@ -873,10 +888,10 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   if ((rc = make_act_map(&ml, A.lo, 1, a.H, 16, G.K, 32))) return rc;
   const int work = a.m_tiles * a.n_tiles;
   const int grid = work < e->sm_count ? work : e->sm_count;
-  if (G.nt == 256)
-    dd::convgen_umma_kernel<256><<<grid, 384, dd::GenCfg<256>::SMEM_BYTES, st>>>(mh, ml, mh, ml, G.mb_hi, G.mb_lo, a);
+  if (nt == 256)
+    dd::convgen_umma_kernel<256><<<grid, 384, dd::GenCfg<256>::SMEM_BYTES, st>>>(mh, ml, mh, ml, mbh, mbl, a);
   else
-    dd::convgen_umma_kernel<192><<<grid, 384, dd::GenCfg<192>::SMEM_BYTES, st>>>(mh, ml, mh, ml, G.mb_hi, G.mb_lo, a);
+    dd::convgen_umma_kernel<192><<<grid, 384, dd::GenCfg<192>::SMEM_BYTES, st>>>(mh, ml, mh, ml, mbh, mbl, a);
   e->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(err));
