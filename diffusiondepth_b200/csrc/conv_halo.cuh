@@ -1,0 +1,340 @@
+// 3x3 / stride 1 / pad 1 convolution on tcgen05 with ROW-HALO REUSE of the activation operand.
+//
+// Measurement (profiles/README.md, round 1): every conv of the DDIM loop moves ~48 KB of operands from L2 into
+// shared memory per pipeline stage and all of them run at the same ~0.7-0.9 us per stage, i.e. they sit on the
+// chip's L2->SM (TMA) bandwidth, not on the tensor pipe.  conv3x3_umma_kernel re-fetches the 128-pixel activation
+// patch once per tap (9x).  Here the output tile is 16 rows x 8 columns and, per 32-channel chunk, the producer
+// fetches three [18 rows][8 cols] column-shifted strips (dx = -1, 0, +1).  For tap (dy, dx) the A operand is strip
+// dx starting dy rows down: its 8-pixel row groups are dense and aligned to the swizzle repeat, so the canonical
+// K-major UMMA descriptor (SBO = 8 rows) addresses it with no copy.  A traffic drops 9 x 128 -> 3 x 144 pixel rows
+// per chunk (2.67x), total L2->SM bytes by 20 % (256->256) to 41 % (256->64).
+//
+// Two TMA rings: A strips (one slot per channel chunk, consumed by 9 taps) and B weight tiles (one slot per
+// (chunk, tap)).  Everything else (3-pass fp16 split, TMEM double buffer, warp roles, epilogues) is as in
+// conv_umma.cuh.  Replaces the same reference lines (ScheduledCNNRefine convs, head :339-359, :321-333).
+#pragma once
+#include "conv_umma.cuh"
+
+namespace dd {
+
+constexpr int HALO_TH = 16;  // output tile: 16 rows x 8 columns = 128 pixels
+constexpr int HALO_TW = 8;
+
+template <int CIN, int COUT, int BK>
+struct HaloCfg {
+  static_assert(CIN % BK == 0 && (BK == 16 || BK == 32), "bad K chunk");
+  static constexpr int KC = CIN / BK;
+  static constexpr int ROW_BYTES = BK * 2;
+  static constexpr int STRIP_ROWS = (HALO_TH + 2) * HALO_TW;        // 144 pixel rows
+  static constexpr int STRIP_BYTES = STRIP_ROWS * ROW_BYTES;        // one plane, one dx
+  static constexpr int STRIP_PAD = (STRIP_BYTES + 1023) / 1024 * 1024;
+  static constexpr int A_SLOT = 6 * STRIP_PAD;                      // 3 dx x (hi, lo)
+  static constexpr int B_TILE = COUT * ROW_BYTES;                   // one plane, one tap, one chunk
+  static constexpr int B_TILE_PAD = (B_TILE + 1023) / 1024 * 1024;
+  static constexpr int B_SLOT = 2 * B_TILE_PAD;
+  static constexpr int A_SLOTS = 2;
+  static constexpr int XPOSE_BYTES = 4 * 32 * 32 * 4;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - XPOSE_BYTES - A_SLOTS * A_SLOT;
+  static constexpr int B_SLOTS_RAW = BUDGET / B_SLOT;
+  static constexpr int B_SLOTS = B_SLOTS_RAW > 8 ? 8 : B_SLOTS_RAW;
+  static_assert(B_SLOTS >= 2, "B ring too small");
+  static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 512 + XPOSE_BYTES;
+  static constexpr int A_TX = 6 * STRIP_BYTES;
+  static constexpr int B_TX = 2 * B_TILE;
+  // Narrow-N layers: back-to-back MMAs into ONE accumulator serialise on its read-modify-write latency (~105 cycles
+  // per MMA measured for N = 64 / 16, vs 32-48 cycles of work).  Give each of the three split passes its own TMEM
+  // accumulator (three independent chains, summed in the epilogue; the small terms also add up separately).
+  static constexpr int NACC = COUT <= 64 ? 3 : 1;
+  static constexpr int ACC_COLS = NACC * COUT;  // TMEM columns per accumulator buffer
+  static constexpr int TMEM_COLS_RAW = 2 * ACC_COLS;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : (TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512)));
+  static constexpr int CH = COUT < 32 ? COUT : 32;
+  static constexpr int GROUP_CH = COUT / 4;
+};
+
+template <int CIN, int COUT, int BK, int EPI>
+__global__ void __launch_bounds__(256, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const ConvArgs p) {
+  using C = HaloCfg<CIN, COUT, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + C::A_SLOTS * C::A_SLOT;
+  uint8_t* ctrl = b_ring + C::B_SLOTS * C::B_SLOT;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* a_empty = a_full + C::A_SLOTS;
+  uint64_t* b_full = a_empty + C::A_SLOTS;
+  uint64_t* b_empty = b_full + C::B_SLOTS;
+  uint64_t* tfull_bar = b_empty + C::B_SLOTS;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [2][4][4][2]
+  float* xpose = reinterpret_cast<float*>(ctrl + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmA_lo);
+    tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&tmB_lo);
+    for (int s = 0; s < C::A_SLOTS; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < C::B_SLOTS; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (A strips)
+    int sa = 0;
+    uint32_t pa = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * HALO_TW, y0 = ty * HALO_TH;
+      for (int kc = 0; kc < C::KC; ++kc) {
+        mbar_wait(&a_empty[sa], pa ^ 1);
+        uint8_t* s = a_ring + sa * C::A_SLOT;
+        mbar_arrive_expect_tx(&a_full[sa], C::A_TX);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          tma_load_4d(s + (2 * dx) * C::STRIP_PAD, &tmA_hi, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
+          tma_load_4d(s + (2 * dx + 1) * C::STRIP_PAD, &tmA_lo, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
+        }
+        if (++sa == C::A_SLOTS) {
+          sa = 0;
+          pa ^= 1;
+        }
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (B weight tiles)
+    int sb = 0;
+    uint32_t pb = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < C::KC; ++kc) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_empty[sb], pb ^ 1);
+          uint8_t* s = b_ring + sb * C::B_SLOT;
+          mbar_arrive_expect_tx(&b_full[sb], C::B_TX);
+          tma_load_3d(s, &tmB_hi, &b_full[sb], kc * BK, 0, tap);
+          tma_load_3d(s + C::B_TILE_PAD, &tmB_lo, &b_full[sb], kc * BK, 0, tap);
+          if (++sb == C::B_SLOTS) {
+            sb = 0;
+            pb ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(TILE_M, COUT);
+    int sa = 0, sb = 0, buf = 0;
+    uint32_t pa = 0, pb = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS);
+      for (int kc = 0; kc < C::KC; ++kc) {
+        mbar_wait(&a_full[sa], pa);
+        const uint32_t a_base = smem_u32(a_ring + sa * C::A_SLOT);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap % 3;
+          mbar_wait(&b_full[sb], pb);
+          tc_fence_after();
+          // strip dx, dy rows down: 8-pixel groups stay dense (8 * ROW_BYTES) and aligned to the swizzle repeat
+          const uint32_t sa_hi = a_base + (2 * dx) * C::STRIP_PAD + dy * HALO_TW * C::ROW_BYTES;
+          const uint32_t sa_lo = sa_hi + C::STRIP_PAD;
+          const uint32_t sb_hi = smem_u32(b_ring + sb * C::B_SLOT);
+          const uint32_t sb_lo = sb_hi + C::B_TILE_PAD;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t a_hi = umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES);
+            const uint64_t a_lo = umma_smem_desc(sa_lo + k * 32, C::ROW_BYTES);
+            const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
+            const uint64_t b_lo = umma_smem_desc(sb_lo + k * 32, C::ROW_BYTES);
+            const uint32_t first = (kc | tap | k) != 0 ? 1u : 0u;
+            if constexpr (C::NACC == 3) {
+              umma_f16(d_tmem, a_lo, b_hi, idesc, first);
+              umma_f16(d_tmem + COUT, a_hi, b_lo, idesc, first);
+              umma_f16(d_tmem + 2 * COUT, a_hi, b_hi, idesc, first);
+            } else {
+              umma_f16(d_tmem, a_lo, b_hi, idesc, first);
+              umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+          }
+          umma_commit(&b_empty[sb]);
+          if (++sb == C::B_SLOTS) {
+            sb = 0;
+            pb ^= 1;
+          }
+        }
+        umma_commit(&a_empty[sa]);
+        if (kc == C::KC - 1) umma_commit(&tfull_bar[buf]);
+        if (++sa == C::A_SLOTS) {
+          sa = 0;
+          pa ^= 1;
+        }
+      }
+      acc_phase ^= (1u << buf);
+      buf ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (as conv_umma.cuh, 16x8 tile)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int r = m >> 3, c = m & 7;
+    uint32_t full_phase = 0;
+    int buf = 0, par = 0;
+    float* T = xpose + q * 1024;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+      const int x = tx * HALO_TW + c, y = ty * HALO_TH + r;
+      const bool valid = (x < p.W) && (y < p.H);
+      const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      const uint32_t row_off = static_cast<uint32_t>(pix * COUT);
+
+      mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
+      full_phase ^= (1u << buf);
+      tc_fence_after();
+
+      float tsum[4] = {0.f, 0.f, 0.f, 0.f}, tsq[4] = {0.f, 0.f, 0.f, 0.f};
+      bool overflow = false;
+#pragma unroll
+      for (int ci = 0; ci < COUT / C::CH; ++ci) {
+        const int ch0 = ci * C::CH;
+        float v[C::CH];
+#pragma unroll
+        for (int j = 0; j < C::CH; ++j) v[j] = 0.f;
+#pragma unroll
+        for (int acc = 0; acc < C::NACC; ++acc) {  // lo*hi + hi*lo first, hi*hi last
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(buf * C::ACC_COLS + acc * COUT + ch0);
+          if constexpr (C::CH == 32) {
+            uint32_t rr[32];
+            tmem_ld_32x32(taddr, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rr[j]);
+          } else {
+            uint32_t rr[16];
+            tmem_ld_32x16(taddr, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(rr[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < C::CH; ++j) v[j] = fmaf(v[j], p.acc_scale, __ldg(p.bias + ch0 + j));
+        if constexpr (EPI == EPI_F32_STATS) {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < C::CH; ++j) {
+              const int g = (ch0 + j) / C::GROUP_CH;
+              tsum[g] += v[j];
+              tsq[g] = fmaf(v[j], v[j], tsq[g]);
+            }
+          }
+        }
+        if constexpr ((EPI == EPI_F32_STATS || EPI == EPI_F32) && C::CH == 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) T[lane * 32 + ((j ^ lane) & 31)] = v[j];
+          __syncwarp();
+#pragma unroll 8
+          for (int rw = 0; rw < 32; ++rw) {
+            const uint32_t o = __shfl_sync(0xffffffffu, row_off, rw) + ch0 + lane;
+            if ((vmask >> rw) & 1u) p.y32[o] = T[rw * 32 + ((lane ^ rw) & 31)];
+          }
+          __syncwarp();
+        } else if (valid) {
+          if constexpr (EPI == EPI_F32_STATS || EPI == EPI_F32) {
+            float4* dst = reinterpret_cast<float4*>(p.y32 + pix * COUT + ch0);
+#pragma unroll
+            for (int j = 0; j < C::CH / 4; ++j)
+              dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            __align__(16) __half hi[C::CH];
+            __align__(16) __half lo[C::CH];
+#pragma unroll
+            for (int j = 0; j < C::CH; ++j) {
+              const float s = v[j] * p.split_scale;
+              overflow |= (fabsf(s) > 60000.f);
+              hi[j] = __float2half_rn(s);
+              lo[j] = __float2half_rn(s - __half2float(hi[j]));
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * COUT + ch0);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + pix * COUT + ch0);
+#pragma unroll
+            for (int j = 0; j < C::CH / 8; ++j) {
+              dh[j] = reinterpret_cast<const uint4*>(hi)[j];
+              dl[j] = reinterpret_cast<const uint4*>(lo)[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+
+      if constexpr (EPI == EPI_F32_STATS) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float s = tsum[g], s2 = tsq[g];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (lane == 0) {
+            red[((par * 4 + q) * 4 + g) * 2 + 0] = s;
+            red[((par * 4 + q) * 4 + g) * 2 + 1] = s2;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int e = threadIdx.x - 128;
+        if (e < 8) {
+          const int g = e >> 1, which = e & 1;
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) t += red[((par * 4 + w) * 4 + g) * 2 + which];
+          p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + which] = t;
+        }
+        par ^= 1;
+      }
+      if constexpr (EPI == EPI_SPLIT) {
+        if (overflow) atomicOr(p.status, 1);
+      }
+      buf ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+}  // namespace dd

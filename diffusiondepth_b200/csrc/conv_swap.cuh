@@ -1,0 +1,231 @@
+// 3x3 conv for the NARROW-N layers of the denoiser (Cout = 64 or 16: noise_embedding.0, pred.0, pred.3) with the
+// operand roles swapped: the WEIGHTS are the UMMA A operand (M = 128 rows = [W_hi(co) for co<64 ; W_lo(co)]) and a
+// 16x16 patch of 256 PIXELS is the B operand (N = 256).
+//
+// Why (measured, profiles/README.md): with pixels as M = 128 and N = Cout <= 64 every tcgen05.mma costs ~105 cycles
+// no matter how little work it does (the 4 KB A-operand fetch from shared memory is the floor), and the 3-pass split
+// needs 3 of them per K-step per 128 pixels: 315 cycles.  Swapped, one MMA D[128 x 256] += [W_hi;W_lo] * P^T covers
+// 256 pixels and BOTH weight planes at the full N = 256 rate; two of them (P = pixel hi plane, pixel lo plane) per
+// K-step give all four partial products (hi*hi, lo*hi in accumulator rows 0..63... and hi*lo, lo*lo in rows 64..127):
+// 2 x ~165 cycles per 256 pixels = 165 per 128 pixels, and the result is exact to the full 22-bit operands.
+//
+// TMEM accumulator: lane = output channel (rows 0..63 from W_hi, 64..127 from W_lo), column = pixel.  The epilogue
+// adds the two halves through shared memory; since lane == channel, each store instruction writes 32 consecutive
+// channels of one pixel: NHWC-coalesced with no transpose.  GroupNorm partial sums: per-thread over its pixels, then
+// a shuffle reduction over the lanes of a group.
+#pragma once
+#include "conv_umma.cuh"
+
+namespace dd {
+
+constexpr int SWAP_TH = 16;  // pixel tile 16 x 16 = 256 = UMMA N
+constexpr int SWAP_TW = 16;
+constexpr int SWAP_N = 256;
+
+template <int CIN, int COUT, int BK>
+struct SwapCfg {
+  static_assert(COUT == 64 || COUT == 16, "swap kernel serves the narrow layers");
+  static_assert(CIN % BK == 0 && (BK == 16 || BK == 32), "bad K chunk");
+  static constexpr int KC = CIN / BK;
+  static constexpr int K_ITERS = 9 * KC;
+  static constexpr int ROW_BYTES = BK * 2;
+  static constexpr int W_BYTES = 128 * ROW_BYTES;        // [W_hi ; W_lo] tile (A operand)
+  static constexpr int P_BYTES = SWAP_N * ROW_BYTES;     // one pixel plane tile (B operand)
+  static constexpr int STAGE_BYTES = W_BYTES + 2 * P_BYTES;
+  static constexpr int XCH_BYTES = 2 * 32 * 33 * 4;      // lo-half exchange: 2 warps x [32 lanes][32 px] (+pad)
+  static constexpr int STAGES_RAW = (220 * 1024 - XCH_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static_assert(STAGES >= 2, "stage too large");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + XCH_BYTES;
+  static constexpr int TMEM_COLS = 512;                  // 2 accumulator buffers x 256 pixel columns
+  static constexpr int GROUP_CH = COUT / 4;
+};
+
+template <int CIN, int COUT, int BK, int EPI>
+__global__ void __launch_bounds__(256, 1)
+conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_constant__ CUtensorMap tmP_lo,
+                    const __grid_constant__ CUtensorMap tmW, const ConvArgs p) {
+  using C = SwapCfg<CIN, COUT, BK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ctrl = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* xch = reinterpret_cast<float*>(ctrl + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmP_hi);
+    tma_prefetch_desc(&tmP_lo);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * SWAP_TW, y0 = ty * SWAP_TH;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        for (int kc = 0; kc < C::KC; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* s = stage_ptr(stage);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_3d(s, &tmW, &full_bar[stage], kc * BK, 0, tap);
+          tma_load_4d(s + C::W_BYTES, &tmP_hi, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+          tma_load_4d(s + C::W_BYTES + C::P_BYTES, &tmP_lo, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(128, SWAP_N);
+    int stage = 0, buf = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * SWAP_N);
+      for (int it = 0; it < C::K_ITERS; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sw = smem_u32(stage_ptr(stage));
+        const uint32_t sp_hi = sw + C::W_BYTES;
+        const uint32_t sp_lo = sp_hi + C::P_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t wd = umma_smem_desc(sw + k * 32, C::ROW_BYTES);
+          const uint64_t ph = umma_smem_desc(sp_hi + k * 32, C::ROW_BYTES);
+          const uint64_t pl = umma_smem_desc(sp_lo + k * 32, C::ROW_BYTES);
+          umma_f16(d_tmem, wd, pl, idesc, (it | k) != 0 ? 1u : 0u);  // small terms first
+          umma_f16(d_tmem, wd, ph, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (it == C::K_ITERS - 1) umma_commit(&tfull_bar[buf]);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc_phase ^= (1u << buf);
+      buf ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: lane = output channel, column = pixel
+    const int q = warp & 3;             // TMEM lane quarter: q = 0,1 hold the W_hi rows (channels 32q..), q = 2,3 the W_lo rows
+    const int ch = (q & 1) * 32 + lane; // output channel of this thread
+    const bool has_ch = ch < COUT;
+    float* X = xch + (q & 1) * (32 * 33);
+    uint32_t full_phase = 0;
+    int buf = 0;
+    const float bias = has_ch ? __ldg(p.bias + ch) : 0.f;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * SWAP_TW, y0 = ty * SWAP_TH;
+      mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
+      full_phase ^= (1u << buf);
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < SWAP_N; c0 += 32) {  // 32 pixels = 2 tile rows
+        uint32_t rr[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * SWAP_N + c0), rr);
+        tmem_ld_wait();
+        if (q >= 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) X[lane * 33 + j] = __uint_as_float(rr[j]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q < 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int m = c0 + j;
+            const int y = y0 + (m >> 4), x = x0 + (m & 15);
+            const bool valid = (y < p.H) && (x < p.W);  // uniform across the warp
+            const float v = fmaf(__uint_as_float(rr[j]) + X[lane * 33 + j], p.acc_scale, bias);
+            if (valid && has_ch) {
+              p.y32[((static_cast<size_t>(img) * p.H + y) * p.W + x) * COUT + ch] = v;
+              s1 += v;
+              s2 = fmaf(v, v, s2);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // X is reused by the next chunk
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if constexpr (EPI == EPI_F32_STATS) {
+        if (q < 2) {
+          // GroupNorm(4, COUT): GROUP_CH consecutive channels = GROUP_CH consecutive lanes
+#pragma unroll
+          for (int o = C::GROUP_CH / 2; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (has_ch && (lane % C::GROUP_CH) == 0) {
+            const int g = ch / C::GROUP_CH;
+            p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + 0] = s1;
+            p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + 1] = s2;
+          }
+        }
+      }
+      buf ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// w [COUT][CIN][3][3] fp32 -> fp16 [tap][128][CIN]: row co = hi(s*w), row 64+co = lo; other rows zero
+__global__ void pack_swap_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin,
+                                        float scale) {
+  const int n = 9 * 128 * cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int ci = i % cin, row = (i / cin) % 128, tap = i / (cin * 128);
+    const int co = row & 63;
+    float r = 0.f;
+    if (co < cout) {
+      const float s = w[(static_cast<size_t>(co) * cin + ci) * 9 + tap] * scale;
+      const __half h = __float2half_rn(s);
+      r = row < 64 ? __half2float(h) : s - __half2float(h);
+    }
+    out[i] = __float2half_rn(r);
+  }
+}
+
+}  // namespace dd

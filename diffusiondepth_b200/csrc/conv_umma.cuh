@@ -63,7 +63,12 @@ struct ConvCfg {
   static constexpr int XPOSE_BYTES = 4 * 32 * 32 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (coalesced y stores)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + scratch*/ + XPOSE_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
-  static constexpr int TMEM_COLS_RAW = 2 * COUT;
+  // Narrow-N layers: back-to-back MMAs into ONE accumulator serialise on its read-modify-write latency (~105 cycles
+  // per MMA measured for N = 64 / 16, vs 32-48 cycles of work).  Give each of the three split passes its own TMEM
+  // accumulator (three independent chains, summed in the epilogue; the small terms also add up separately).
+  static constexpr int NACC = COUT <= 64 ? 3 : 1;
+  static constexpr int ACC_COLS = NACC * COUT;  // TMEM columns per accumulator buffer
+  static constexpr int TMEM_COLS_RAW = 2 * ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : (TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512)));
   static constexpr int CH = COUT < 32 ? COUT : 32;    // epilogue column chunk
   static constexpr int GROUP_CH = COUT / 4;           // GroupNorm(4, COUT)
@@ -94,7 +99,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     tma_prefetch_desc(&tmB_hi);
     tma_prefetch_desc(&tmB_lo);
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);  // two producer threads (activations / weights) arrive per stage
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -114,8 +119,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
   auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if ((warp == 0 || warp == 3) && lane == 0) {
+    // ------------------------------------------------------------------ TMA producers: warp 0 feeds the activation
+    // planes, warp 3 the weight planes (a single thread issuing all four bulk-tensor copies per stage was the
+    // pipeline's bottleneck: ~160 ns per issued copy)
+    const bool act = (warp == 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -128,11 +136,15 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int kc = 0; kc < C::KC; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = stage_ptr(stage);
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_4d(s, &tmA_hi, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
-          tma_load_4d(s + C::A_BYTES, &tmA_lo, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
-          tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * BK, 0, tap);
-          tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * BK, 0, tap);
+          if (act) {
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
+            tma_load_4d(s, &tmA_hi, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+            tma_load_4d(s + C::A_BYTES, &tmA_lo, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_BYTES);
+            tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * BK, 0, tap);
+            tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * BK, 0, tap);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -150,7 +162,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * COUT);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS);
       for (int it = 0; it < C::K_ITERS; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -164,9 +176,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint64_t a_lo = umma_smem_desc(sa_lo + k * 32, C::ROW_BYTES);
           const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
           const uint64_t b_lo = umma_smem_desc(sb_lo + k * 32, C::ROW_BYTES);
-          umma_f16(d_tmem, a_lo, b_hi, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
-          umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+          const uint32_t first = (it | k) != 0 ? 1u : 0u;
+          if constexpr (C::NACC == 3) {
+            umma_f16(d_tmem, a_lo, b_hi, idesc, first);
+            umma_f16(d_tmem + COUT, a_hi, b_lo, idesc, first);
+            umma_f16(d_tmem + 2 * COUT, a_hi, b_hi, idesc, first);
+          } else {
+            umma_f16(d_tmem, a_lo, b_hi, idesc, first);
+            umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
         }
         umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
         if (it == C::K_ITERS - 1) umma_commit(&tfull_bar[buf]);
@@ -207,21 +226,24 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       for (int ci = 0; ci < COUT / C::CH; ++ci) {
         const int ch0 = ci * C::CH;
         float v[C::CH];
-        {
-          const uint32_t taddr =
-              tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * COUT + ch0);
+#pragma unroll
+        for (int j = 0; j < C::CH; ++j) v[j] = 0.f;
+#pragma unroll
+        for (int acc = 0; acc < C::NACC; ++acc) {  // lo*hi + hi*lo first, hi*hi last
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 static_cast<uint32_t>(buf * C::ACC_COLS + acc * COUT + ch0);
           if constexpr (C::CH == 32) {
             uint32_t rr[32];
             tmem_ld_32x32(taddr, rr);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(rr[j]);
           } else {
             uint32_t rr[16];
             tmem_ld_32x16(taddr, rr);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
+            for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(rr[j]);
           }
         }
 #pragma unroll

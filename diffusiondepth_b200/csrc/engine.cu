@@ -15,6 +15,8 @@
 #include "../../include/dd_engine.h"
 #include "kernels.cuh"
 #include "convgen.cuh"
+#include "conv_halo.cuh"
+#include "conv_swap.cuh"
 #include "swin.cuh"
 
 namespace {
@@ -62,6 +64,30 @@ int make_act_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+  return DD_OK;
+}
+// activation strip for the halo kernel: box = {bk, 8, 18, 1}
+int make_strip_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C, int bk) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, dd::HALO_TW, dd::HALO_TH + 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(strip) failed: " + std::to_string((int)r));
+  return DD_OK;
+}
+// 16x16 pixel patch for the swapped-operand kernel: box = {bk, 16, 16, 1}
+int make_patch_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C, int bk) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, dd::SWAP_TW, dd::SWAP_TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(patch) failed: " + std::to_string((int)r));
   return DD_OK;
 }
 // weights: [9][COUT][CIN] fp16; box = {bk, COUT, 1}
@@ -136,6 +162,64 @@ cudaError_t launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
   kern<<<grid, 256, C::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, args);
   return cudaGetLastError();
 }
+constexpr int kHaloBK[5] = {16, 32, 32, 32, 32};  // K chunk of the halo kernel per shape id
+constexpr int kSwapBK[5] = {16, 0, 0, 32, 32};    // K chunk of the swapped-operand kernel (narrow-N shapes only)
+// Which kernel serves which shape inside the engine when the flags allow it (measured, profiles/README.md): the
+// swapped-operand kernel wins only where the mainloop dominates (256->64); the two tiny layers are epilogue-bound
+// and stay on the classic kernel; row-halo reuse pays for the wide layers.
+constexpr bool kUseSwap[5] = {false, false, false, true, false};
+constexpr bool kUseHalo[5] = {false, true, true, false, false};
+template <int CIN, int COUT, int BK, int EPI>
+cudaError_t launch_swap(const CUtensorMap& p_hi, const CUtensorMap& p_lo, const CUtensorMap& w, const dd::ConvArgs& args,
+                        int sm_count, cudaStream_t st) {
+  using C = dd::SwapCfg<CIN, COUT, BK>;
+  int grid = args.num_tiles < sm_count ? args.num_tiles : sm_count;
+  dd::conv3x3_swap_kernel<CIN, COUT, BK, EPI><<<grid, 256, C::SMEM_BYTES, st>>>(p_hi, p_lo, w, args);
+  return cudaGetLastError();
+}
+template <int CIN, int COUT, int BK>
+cudaError_t configure_swap() {
+  using C = dd::SwapCfg<CIN, COUT, BK>;
+  cudaError_t e = cudaFuncSetAttribute(dd::conv3x3_swap_kernel<CIN, COUT, BK, dd::EPI_F32_STATS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dd::conv3x3_swap_kernel<CIN, COUT, BK, dd::EPI_F32>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+}
+cudaError_t configure_swap_kernels() {
+  cudaError_t e;
+  if ((e = configure_swap<16, 64, 16>()) != cudaSuccess) return e;
+  if ((e = configure_swap<256, 64, 32>()) != cudaSuccess) return e;
+  return configure_swap<64, 16, 32>();
+}
+template <int CIN, int COUT, int BK, int EPI>
+cudaError_t launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                        const CUtensorMap& b_lo, const dd::ConvArgs& args, int sm_count, cudaStream_t st) {
+  using C = dd::HaloCfg<CIN, COUT, BK>;
+  int grid = args.num_tiles < sm_count ? args.num_tiles : sm_count;
+  dd::conv3x3_halo_kernel<CIN, COUT, BK, EPI><<<grid, 256, C::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, args);
+  return cudaGetLastError();
+}
+template <int CIN, int COUT, int BK>
+cudaError_t configure_halo_all_epi() {
+  using C = dd::HaloCfg<CIN, COUT, BK>;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<CIN, COUT, BK, dd::EPI_F32_STATS>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<CIN, COUT, BK, dd::EPI_SPLIT>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dd::conv3x3_halo_kernel<CIN, COUT, BK, dd::EPI_F32>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+}
+cudaError_t configure_halo_kernels() {
+  cudaError_t e;
+  if ((e = configure_halo_all_epi<16, 64, 16>()) != cudaSuccess) return e;
+  if ((e = configure_halo_all_epi<64, 256, 32>()) != cudaSuccess) return e;
+  if ((e = configure_halo_all_epi<256, 256, 32>()) != cudaSuccess) return e;
+  if ((e = configure_halo_all_epi<256, 64, 32>()) != cudaSuccess) return e;
+  return configure_halo_all_epi<64, 16, 32>();
+}
+
 template <int CIN, int COUT, int EPI>
 cudaError_t launch_simt(const dd::SimtArgs& a, cudaStream_t st) {
   constexpr int CO_T = COUT < 64 ? COUT : 64;
@@ -152,6 +236,9 @@ struct ConvLayer {
   float* bias = nullptr;
   float wscale = 1.f;
   CUtensorMap mb_hi, mb_lo;
+  CUtensorMap mh_hi, mh_lo;  // same planes, box for the halo kernel's K chunk
+  __half* w_swap = nullptr;  // [9][128][CIN]: rows co = hi, 64+co = lo (swapped-operand kernel, narrow layers)
+  CUtensorMap mw_swap;
 };
 
 struct Raw {
@@ -237,6 +324,7 @@ struct dd_engine {
   float *x32 = nullptr, *Y = nullptr, *cond = nullptr, *stats[4] = {}, *mr[4] = {}, *temb_sel = nullptr;
   __half *xs_hi = nullptr, *xs_lo = nullptr, *S_hi[2] = {}, *S_lo[2] = {};
   int* status = nullptr;
+  int stats_tiles_img[4] = {0, 0, 0, 0};  // tiles per image of the kernel that last filled stats[i]
   // graph
   Producers prod;
   Backbone bb;
@@ -268,7 +356,8 @@ struct Carver {
 };
 
 struct Geom {
-  int B, h, w, P, tiles_x, tiles_y, tiles_img, tiles;
+  int B, h, w, P, tiles_x, tiles_y, tiles_img, tiles;  // tiles of the conv kernel selected by cfg.flags
+  int tiles_max;                                       // max over both tilings (buffer sizing)
 };
 Geom geom_of(const dd_config& c) {
   Geom g;
@@ -276,10 +365,13 @@ Geom geom_of(const dd_config& c) {
   g.h = c.latent_h;
   g.w = c.latent_w;
   g.P = g.h * g.w;
+  const int t816 = ((g.w + dd::TILE_W - 1) / dd::TILE_W) * ((g.h + dd::TILE_H - 1) / dd::TILE_H);
+  const int t168 = ((g.w + dd::HALO_TW - 1) / dd::HALO_TW) * ((g.h + dd::HALO_TH - 1) / dd::HALO_TH);
   g.tiles_x = (g.w + dd::TILE_W - 1) / dd::TILE_W;
   g.tiles_y = (g.h + dd::TILE_H - 1) / dd::TILE_H;
   g.tiles_img = g.tiles_x * g.tiles_y;
   g.tiles = g.tiles_img * g.B;
+  g.tiles_max = (t816 > t168 ? t816 : t168) * g.B;
   return g;
 }
 
@@ -301,7 +393,7 @@ size_t carve(dd_engine* e, void* base) {
   }
   v->cond = c.take<float>(static_cast<size_t>(g.B) * e->cfg.cond_h * e->cfg.cond_w * 256);
   for (int i = 0; i < 4; ++i) {
-    v->stats[i] = c.take<float>(static_cast<size_t>(g.tiles) * 8);
+    v->stats[i] = c.take<float>(static_cast<size_t>(g.tiles_max) * 8);
     v->mr[i] = c.take<float>(static_cast<size_t>(g.B) * 8);
   }
   v->temb_sel = c.take<float>(static_cast<size_t>(g.B) * 256);
@@ -364,7 +456,40 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
   a.status = e->status;
   cudaError_t err = cudaSuccess;
   e->launches++;
-  if (e->cfg.flags & DD_FLAG_SIMT_CONV) {
+  int which = -1;
+  for (int i = 0; i < 4; ++i)
+    if (stats_partial == e->stats[i]) which = i;
+  if (which >= 0) e->stats_tiles_img[which] = g.tiles_img;
+  const bool use_swap = (e->cfg.flags & DD_FLAG_SWAP_NARROW) && !(e->cfg.flags & DD_FLAG_SIMT_CONV) &&
+                        kUseSwap[L.sid] && epi != dd::EPI_SPLIT;
+  const bool use_halo = (e->cfg.flags & DD_FLAG_HALO_CONV) && !(e->cfg.flags & DD_FLAG_SIMT_CONV) && kUseHalo[L.sid];
+  if (!use_swap) {  // tile geometry of the kernel actually launched
+    const int tw = use_halo ? dd::HALO_TW : dd::TILE_W, th = use_halo ? dd::HALO_TH : dd::TILE_H;
+    a.tiles_x = (g.w + tw - 1) / tw;
+    a.tiles_y = (g.h + th - 1) / th;
+    a.num_tiles = a.tiles_x * a.tiles_y * g.B;
+    if (which >= 0) e->stats_tiles_img[which] = a.tiles_x * a.tiles_y;
+  }
+  if (use_swap) {
+    a.tiles_x = (g.w + dd::SWAP_TW - 1) / dd::SWAP_TW;
+    a.tiles_y = (g.h + dd::SWAP_TH - 1) / dd::SWAP_TH;
+    a.num_tiles = a.tiles_x * a.tiles_y * g.B;
+    if (which >= 0) e->stats_tiles_img[which] = a.tiles_x * a.tiles_y;
+    CUtensorMap mp_hi, mp_lo;
+    int rc;
+    const int bk = kSwapBK[L.sid];
+    if ((rc = make_patch_map(&mp_hi, in_hi, g.B, g.h, g.w, s.cin, bk))) return rc;
+    if ((rc = make_patch_map(&mp_lo, in_lo, g.B, g.h, g.w, s.cin, bk))) return rc;
+    const bool st_ = (epi == dd::EPI_F32_STATS);
+    switch (L.sid) {
+      case 0: err = st_ ? launch_swap<16, 64, 16, dd::EPI_F32_STATS>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st)
+                        : launch_swap<16, 64, 16, dd::EPI_F32>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st); break;
+      case 3: err = st_ ? launch_swap<256, 64, 32, dd::EPI_F32_STATS>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st)
+                        : launch_swap<256, 64, 32, dd::EPI_F32>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st); break;
+      case 4: err = st_ ? launch_swap<64, 16, 32, dd::EPI_F32_STATS>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st)
+                        : launch_swap<64, 16, 32, dd::EPI_F32>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st); break;
+    }
+  } else if (e->cfg.flags & DD_FLAG_SIMT_CONV) {
     dd::SimtArgs sa;
     sa.in_hi = in_hi;
     sa.in_lo = in_lo;
@@ -385,6 +510,28 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
       SIMT_CASE(4, 64, 16)
     }
 #undef SIMT_CASE
+  } else if (use_halo) {
+    CUtensorMap ma_hi, ma_lo;
+    int rc;
+    const int hbk = kHaloBK[L.sid];
+    if ((rc = make_strip_map(&ma_hi, in_hi, g.B, g.h, g.w, s.cin, hbk))) return rc;
+    if ((rc = make_strip_map(&ma_lo, in_lo, g.B, g.h, g.w, s.cin, hbk))) return rc;
+#define HALO_CASE(ID, CI, CO, BK)                                                                                   \
+  case ID:                                                                                                          \
+    err = (epi == dd::EPI_F32_STATS)                                                                                \
+              ? launch_halo<CI, CO, BK, dd::EPI_F32_STATS>(ma_hi, ma_lo, L.mh_hi, L.mh_lo, a, e->sm_count, st)      \
+          : (epi == dd::EPI_SPLIT)                                                                                  \
+              ? launch_halo<CI, CO, BK, dd::EPI_SPLIT>(ma_hi, ma_lo, L.mh_hi, L.mh_lo, a, e->sm_count, st)          \
+              : launch_halo<CI, CO, BK, dd::EPI_F32>(ma_hi, ma_lo, L.mh_hi, L.mh_lo, a, e->sm_count, st);           \
+    break;
+    switch (L.sid) {
+      HALO_CASE(0, 16, 64, 16)
+      HALO_CASE(1, 64, 256, 32)
+      HALO_CASE(2, 256, 256, 32)
+      HALO_CASE(3, 256, 64, 32)
+      HALO_CASE(4, 64, 16, 32)
+    }
+#undef HALO_CASE
   } else {
     CUtensorMap ma_hi, ma_lo;
     int rc;
@@ -414,7 +561,7 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
 int run_finalize(dd_engine* e, int which, int channels, cudaStream_t st) {
   const Geom g = geom_of(e->cfg);
   const double inv = 1.0 / (static_cast<double>(g.P) * (channels / 4));
-  dd::gn_finalize_kernel<<<g.B * 4, 256, 0, st>>>(e->stats[which], g.tiles_img, inv, 1e-5f, e->mr[which]);
+  dd::gn_finalize_kernel<<<g.B * 4, 256, 0, st>>>(e->stats[which], e->stats_tiles_img[which], inv, 1e-5f, e->mr[which]);
   e->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("gn_finalize: ") + cudaGetErrorString(err));
@@ -607,6 +754,14 @@ int pack_layer(dd_engine* e, ConvLayer& L, const float* w, const float* b, int c
   const ShapeInfo s = kShapes[L.sid];
   if ((rc = make_w_map(&L.mb_hi, L.w_hi, cout, cin, s.bk))) return rc;
   if ((rc = make_w_map(&L.mb_lo, L.w_lo, cout, cin, s.bk))) return rc;
+  if ((rc = make_w_map(&L.mh_hi, L.w_hi, cout, cin, kHaloBK[L.sid]))) return rc;
+  if ((rc = make_w_map(&L.mh_lo, L.w_lo, cout, cin, kHaloBK[L.sid]))) return rc;
+  if (kSwapBK[L.sid] > 0) {
+    if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_swap), static_cast<size_t>(9) * 128 * cin * 2))) return rc;
+    dd::pack_swap_weight_kernel<<<128, 256, 0, st>>>(w, L.w_swap, cout, cin, scale);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = make_w_map(&L.mw_swap, L.w_swap, 128, cin, kSwapBK[L.sid]))) return rc;
+  }
   return DD_OK;
 }
 
@@ -1004,7 +1159,8 @@ int dd_create(const dd_config* cfg, dd_handle* out) {
   e->sm_count = prop.multiProcessorCount;
   if (cudaMallocHost(&e->status_host, 64) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      configure_all_kernels() != cudaSuccess) {
+      configure_all_kernels() != cudaSuccess || configure_halo_kernels() != cudaSuccess ||
+      configure_swap_kernels() != cudaSuccess) {
     std::string msg = std::string("engine setup failed: ") + cudaGetErrorString(cudaGetLastError());
     if (e->status_host) cudaFreeHost(e->status_host);
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
@@ -1481,6 +1637,7 @@ size_t dd_conv3x3_workspace_bytes(int32_t batch, int32_t cin, int32_t cout, int3
   add(nw * 2);
   add(nw * 2);
   add(nw * 4);
+  add(static_cast<size_t>(9) * 128 * cin * 2);  // swapped-operand weight tile
   return align_up(off, 1024);
 }
 
@@ -1505,6 +1662,7 @@ int dd_conv3x3(dd_handle h, const float* x, const float* w, const float* b, floa
   __half* whi = c.take<__half>(nw);
   __half* wlo = c.take<__half>(nw);
   float* wsimt = c.take<float>(nw);
+  __half* wswap = c.take<__half>(static_cast<size_t>(9) * 128 * cin);
   CUDA_TRY(cudaMemsetAsync(status, 0, 64, st));
   int rc;
   if ((rc = transpose_in(x, xn, batch, cin, height * width, st))) return rc;
@@ -1551,6 +1709,40 @@ int dd_conv3x3(dd_handle h, const float* x, const float* w, const float* b, floa
       case 2: err = launch_simt<256, 256, dd::EPI_F32>(sa, st); break;
       case 3: err = launch_simt<256, 64, dd::EPI_F32>(sa, st); break;
       case 4: err = launch_simt<64, 16, dd::EPI_F32>(sa, st); break;
+    }
+  } else if ((h->cfg.flags & DD_FLAG_SWAP_NARROW) && kSwapBK[sid] > 0) {
+    CUtensorMap mp_hi, mp_lo, mw;
+    const int bk = kSwapBK[sid];
+    a.tiles_x = (width + dd::SWAP_TW - 1) / dd::SWAP_TW;
+    a.tiles_y = (height + dd::SWAP_TH - 1) / dd::SWAP_TH;
+    a.num_tiles = a.tiles_x * a.tiles_y * batch;
+    __half* wsw = wswap;
+    dd::pack_swap_weight_kernel<<<128, 256, 0, st>>>(w, wsw, cout, cin, sw);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = make_patch_map(&mp_hi, hi, batch, height, width, cin, bk))) return rc;
+    if ((rc = make_patch_map(&mp_lo, lo, batch, height, width, cin, bk))) return rc;
+    if ((rc = make_w_map(&mw, wsw, 128, cin, bk))) return rc;
+    switch (sid) {
+      case 0: err = launch_swap<16, 64, 16, dd::EPI_F32>(mp_hi, mp_lo, mw, a, h->sm_count, st); break;
+      case 3: err = launch_swap<256, 64, 32, dd::EPI_F32>(mp_hi, mp_lo, mw, a, h->sm_count, st); break;
+      case 4: err = launch_swap<64, 16, 32, dd::EPI_F32>(mp_hi, mp_lo, mw, a, h->sm_count, st); break;
+    }
+  } else if (h->cfg.flags & DD_FLAG_HALO_CONV) {
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    const int hbk = kHaloBK[sid];
+    a.tiles_x = (width + dd::HALO_TW - 1) / dd::HALO_TW;
+    a.tiles_y = (height + dd::HALO_TH - 1) / dd::HALO_TH;
+    a.num_tiles = a.tiles_x * a.tiles_y * batch;
+    if ((rc = make_strip_map(&ma_hi, hi, batch, height, width, cin, hbk))) return rc;
+    if ((rc = make_strip_map(&ma_lo, lo, batch, height, width, cin, hbk))) return rc;
+    if ((rc = make_w_map(&mb_hi, whi, cout, cin, hbk))) return rc;
+    if ((rc = make_w_map(&mb_lo, wlo, cout, cin, hbk))) return rc;
+    switch (sid) {
+      case 0: err = launch_halo<16, 64, 16, dd::EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, a, h->sm_count, st); break;
+      case 1: err = launch_halo<64, 256, 32, dd::EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, a, h->sm_count, st); break;
+      case 2: err = launch_halo<256, 256, 32, dd::EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, a, h->sm_count, st); break;
+      case 3: err = launch_halo<256, 64, 32, dd::EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, a, h->sm_count, st); break;
+      case 4: err = launch_halo<64, 16, 32, dd::EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, a, h->sm_count, st); break;
     }
   } else {
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;

@@ -65,7 +65,9 @@ enum dd_variant {
 enum dd_flags {
   DD_FLAG_CUDA_GRAPH = 1 << 0, /* capture the T-step loop once and replay it */
   DD_FLAG_SIMT_CONV = 1 << 1,  /* debug: fp32 CUDA-core convolutions instead of tcgen05 */
-  DD_FLAG_CHECK_RANGE = 1 << 2 /* after the call, sync and report DD_ERR_RANGE if the split overflowed */
+  DD_FLAG_CHECK_RANGE = 1 << 2,/* after the call, sync and report DD_ERR_RANGE if the split overflowed */
+  DD_FLAG_HALO_CONV = 1 << 3,  /* loop convs on the row-halo-reuse kernel (16x8 tiles, 2.7x less activation traffic) */
+  DD_FLAG_SWAP_NARROW = 1 << 4 /* Cout <= 64 convs on the swapped-operand kernel (weights as A, 256 pixels as N) */
 };
 
 typedef struct dd_config {
