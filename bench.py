@@ -212,9 +212,10 @@ def main():
         P = B * ((H + 1) // 2) * ((W + 1) // 2)
         flops = 2.0 * P * cout * 9 * cin  # algorithmic (one fp32-grade product-sum per MAC), not the 3x issued
         ach = flops / (kms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": f"conv3x3_umma_kernel<{cin},{cout}>", "achieved": ach, "peak": pk["tf_burst"],
+        roof = {"bound": "tensor", "kernel": (f"conv3x3_halo_kernel<{cin},{cout},32>" if cout == 256 else f"conv3x3_swap_kernel<{cin},{cout},32>"), "achieved": ach, "peak": pk["tf_burst"],
                 "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "issued_frac": 3 * ach / pk["tf_burst"],
-                "ms_per_launch": kms, "traffic": None, "peak_source": pk["source"] + ", bf16 burst",
+                "ms_per_launch": kms, "traffic": (831.5e6 if (cin, cout) == (256, 256) and args.workload == "C3" else None),
+                "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r01_loop_convs_ncu_full_summary.csv); algorithmic 876.6e6", "peak_source": pk["source"] + ", bf16 burst",
                 "note": "achieved = algorithmic FLOPs; the 3-pass fp16 split issues 3x that on the tensor pipe, so 1/3 is the ceiling"}
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
