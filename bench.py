@@ -162,8 +162,10 @@ def main():
         return shard.gather_depth(pred, B * world) if world > 1 else pred
 
     def step_e2e():
+        # the call a user of the reference makes (src/main.py:456-470): host sample -> device -> net(sample) -> host;
+        # the initial latent is drawn on the device by the head, exactly as the reference does (head :283)
         with torch.no_grad():
-            out = model({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+            out = model({k: v.to(dev, non_blocking=True) for k, v in host.items() if k != "noise"})
         pred = shard.gather_depth(out["pred"], B * world) if world > 1 else out["pred"]
         return pred[first:first + B].to("cpu", non_blocking=False)
 
@@ -199,7 +201,7 @@ def main():
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "noise")
     d2h = B * H * W * 4
 
     # roofline of the dominant kernel: the 256->256 3x3 conv (convA/convB = 79 % of the loop's FLOPs)

@@ -32,7 +32,7 @@ struct SwapCfg {
   static constexpr int W_BYTES = 128 * ROW_BYTES;        // [W_hi ; W_lo] tile (A operand)
   static constexpr int P_BYTES = SWAP_N * ROW_BYTES;     // one pixel plane tile (B operand)
   static constexpr int STAGE_BYTES = W_BYTES + 2 * P_BYTES;
-  static constexpr int XCH_BYTES = 2 * 32 * 33 * 4;      // lo-half exchange: 2 warps x [32 lanes][32 px] (+pad)
+  static constexpr int XCH_BYTES = 4 * 32 * 33 * 4 + 2 * 32 * 2 * 4;  // 2 pairs x 2 parities x [32 lanes][32 px (+pad)] + stats scratch
   static constexpr int STAGES_RAW = (220 * 1024 - XCH_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static_assert(STAGES >= 2, "stage too large");
@@ -140,13 +140,18 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
       buf ^= 1;
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: lane = output channel, column = pixel
-    const int q = warp & 3;             // TMEM lane quarter: q = 0,1 hold the W_hi rows (channels 32q..), q = 2,3 the W_lo rows
-    const int ch = (q & 1) * 32 + lane; // output channel of this thread
+    // ------------------------------------------------------------------ epilogue: lane = output channel, column = pixel.
+    // TMEM lane quarters q = 0,1 hold the W_hi rows (channels 32q + lane), q = 2,3 the W_lo rows of the same channels.
+    // Per 32-pixel chunk (= 2 tile rows of 16) the two halves swap 16 pixels each through shared memory, so that all
+    // four warps add and store: q < 2 finish pixels 0..15 of the chunk, q >= 2 pixels 16..31.  Double-buffered exchange
+    // tile -> one named barrier per chunk.
+    const int q = warp & 3;
+    const int ch = (q & 1) * 32 + lane;
     const bool has_ch = ch < COUT;
-    float* X = xch + (q & 1) * (32 * 33);
+    const bool upper = q >= 2;           // which half of the chunk's pixels this warp finishes
+    float* Xbase = xch + (q & 1) * (2 * 32 * 33);  // [parity][lane][32 (+1 pad)]
     uint32_t full_phase = 0;
-    int buf = 0;
+    int buf = 0, par = 0;
     const float bias = has_ch ? __ldg(p.bias + ch) : 0.f;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
@@ -155,48 +160,53 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
       full_phase ^= (1u << buf);
       tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
+      const uint32_t xmask = (x0 + 16 <= p.W) ? 0xFFFFu : ((1u << (p.W - x0)) - 1u);  // valid columns of this tile
 #pragma unroll 1
-      for (int c0 = 0; c0 < SWAP_N; c0 += 32) {  // 32 pixels = 2 tile rows
+      for (int c0 = 0; c0 < SWAP_N; c0 += 32) {
         uint32_t rr[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * SWAP_N + c0), rr);
         tmem_ld_wait();
-        if (q >= 2) {
+        float* X = Xbase + par * (32 * 33);
+        // hand the partner the 16 pixels it will finish: hi-warps give pixels 16..31, lo-warps give pixels 0..15
 #pragma unroll
-          for (int j = 0; j < 32; ++j) X[lane * 33 + j] = __uint_as_float(rr[j]);
-        }
+        for (int j = 0; j < 16; ++j) X[lane * 33 + (upper ? j : 16 + j)] = __uint_as_float(rr[upper ? j : 16 + j]);
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (q < 2) {
+        const int y = y0 + (c0 >> 4) + (upper ? 1 : 0);  // chunk = two tile rows; this warp owns one of them
+        if (y < p.H && has_ch) {
+          float* dst = p.y32 + ((static_cast<size_t>(img) * p.H + y) * p.W + x0) * COUT + ch;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int m = c0 + j;
-            const int y = y0 + (m >> 4), x = x0 + (m & 15);
-            const bool valid = (y < p.H) && (x < p.W);  // uniform across the warp
-            const float v = fmaf(__uint_as_float(rr[j]) + X[lane * 33 + j], p.acc_scale, bias);
-            if (valid && has_ch) {
-              p.y32[((static_cast<size_t>(img) * p.H + y) * p.W + x) * COUT + ch] = v;
+          for (int j = 0; j < 16; ++j) {
+            const int jj = upper ? 16 + j : j;
+            const float v = fmaf(__uint_as_float(rr[jj]) + X[lane * 33 + jj], p.acc_scale, bias);
+            if ((xmask >> j) & 1u) {
+              dst[j * COUT] = v;
               s1 += v;
               s2 = fmaf(v, v, s2);
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // X is reused by the next chunk
+        par ^= 1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
       if constexpr (EPI == EPI_F32_STATS) {
-        if (q < 2) {
-          // GroupNorm(4, COUT): GROUP_CH consecutive channels = GROUP_CH consecutive lanes
+        // GroupNorm(4, COUT): GROUP_CH consecutive channels = consecutive lanes; then add the two pixel halves
 #pragma unroll
-          for (int o = C::GROUP_CH / 2; o > 0; o >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-          }
-          if (has_ch && (lane % C::GROUP_CH) == 0) {
-            const int g = ch / C::GROUP_CH;
-            p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + 0] = s1;
-            p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + 1] = s2;
-          }
+        for (int o = C::GROUP_CH / 2; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        float* R = xch + 4 * 32 * 33;  // [2 (q&1)][32 lanes][2] scratch for the lo-warps' sums
+        if (upper) {
+          R[((q & 1) * 32 + lane) * 2 + 0] = s1;
+          R[((q & 1) * 32 + lane) * 2 + 1] = s2;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!upper && has_ch && (lane % C::GROUP_CH) == 0) {
+          const int g = ch / C::GROUP_CH;
+          p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + 0] = s1 + R[((q & 1) * 32 + lane) * 2 + 0];
+          p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + 1] = s2 + R[((q & 1) * 32 + lane) * 2 + 1];
         }
       }
       buf ^= 1;
