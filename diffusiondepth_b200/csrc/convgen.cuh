@@ -22,6 +22,9 @@ struct GenConvArgs {
   float acc_scale;
   int relu;           // activation: 0 none, 1 ReLU, 2 exact (erf) GELU
   int m_valid;        // > 0: GEMM mode (B = 1, W = 16): only "pixels" (tokens) with index < m_valid are stored
+  int stride;         // 1 or 2: input pixel of output (y, x), tap (dy, dx) is (stride*y + dy, stride*x + dx); the A tensor
+                      // maps are then built with elementStrides = stride so one box still delivers 8 x 16 pixels
+  int add_first;      // 1: addend is added BEFORE the activation (ResNet residual), 0: after it (FPN top-down add)
   int shuffle;        // 1: ConvTranspose2d(k=2,s=2): channel n = q*(cout/4)+c goes to pixel (2y+q/2, 2x+q%2), channel c
   float* y32;         // optional fp32 NHWC output
   const float* add32; // optional fp32 NHWC addend (indexed like y32), added after the ReLU
@@ -45,7 +48,7 @@ struct GenCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + XPOSE_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   static constexpr int TMEM_COLS = 512;
-  static_assert(NT % 32 == 0 && NT <= 256 && 2 * NT <= 512, "bad N tile");
+  static_assert(NT % 32 == 0 && NT <= 256 && 2 * NT <= 512, "bad N tile");  // instantiated: 64, 128, 192, 256
 };
 
 template <int NT>
@@ -108,12 +111,13 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = stage_ptr(stage);
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int ax = x0 * p.stride + dx, ay = y0 * p.stride + dy;
           if (kc < p.kc0) {
-            tma_load_4d(s, &tmA0_hi, &full_bar[stage], kc * C::BK, x0 + dx, y0 + dy, img);
-            tma_load_4d(s + C::A_BYTES, &tmA0_lo, &full_bar[stage], kc * C::BK, x0 + dx, y0 + dy, img);
+            tma_load_4d(s, &tmA0_hi, &full_bar[stage], kc * C::BK, ax, ay, img);
+            tma_load_4d(s + C::A_BYTES, &tmA0_lo, &full_bar[stage], kc * C::BK, ax, ay, img);
           } else {
-            tma_load_4d(s, &tmA1_hi, &full_bar[stage], (kc - p.kc0) * C::BK, x0 + dx, y0 + dy, img);
-            tma_load_4d(s + C::A_BYTES, &tmA1_lo, &full_bar[stage], (kc - p.kc0) * C::BK, x0 + dx, y0 + dy, img);
+            tma_load_4d(s, &tmA1_hi, &full_bar[stage], (kc - p.kc0) * C::BK, ax, ay, img);
+            tma_load_4d(s + C::A_BYTES, &tmA1_lo, &full_bar[stage], (kc - p.kc0) * C::BK, ax, ay, img);
           }
           tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * C::BK, nt * NT, tap);
           tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * C::BK, nt * NT, tap);
@@ -220,9 +224,11 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
             for (int k = 0; k < 8; ++k) {
               if (!((vmask >> (r0 + k)) & 1u)) continue;  // warp-uniform
               float t = fmaf(T[(r0 + k) * 32 + ((lane ^ (r0 + k)) & 31)], p.acc_scale, sh);
+              if (p.add_first) t += ad[k];
               if (p.relu == 1) t = fmaxf(t, 0.f);
               else if (p.relu == 2) t = 0.5f * t * (1.f + erff(t * 0.70710678118654752f));
-              if (p.y32) p.y32[o[k]] = t + ad[k];
+              if (!p.add_first) t += ad[k];
+              if (p.y32) p.y32[o[k]] = t;
             }
           }
           __syncwarp();
@@ -230,22 +236,29 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           // row-per-thread path (fp16 plane outputs: 64 contiguous bytes per row and plane)
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float t = fmaf(__uint_as_float(rr[j]), p.acc_scale, __ldg(p.shift + n0 + j));
-            if (p.relu == 1) t = fmaxf(t, 0.f);
-            else if (p.relu == 2) t = 0.5f * t * (1.f + erff(t * 0.70710678118654752f));
-            v[j] = t;
-          }
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rr[j]), p.acc_scale, __ldg(p.shift + n0 + j));
+          float ad[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ad[j] = 0.f;
           if (p.add32) {
             const float4* a4 = reinterpret_cast<const float4*>(p.add32 + o_lane);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 t = __ldg(a4 + j);
-              v[4 * j] += t.x;
-              v[4 * j + 1] += t.y;
-              v[4 * j + 2] += t.z;
-              v[4 * j + 3] += t.w;
+              ad[4 * j] = t.x;
+              ad[4 * j + 1] = t.y;
+              ad[4 * j + 2] = t.z;
+              ad[4 * j + 3] = t.w;
             }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = v[j];
+            if (p.add_first) t += ad[j];
+            if (p.relu == 1) t = fmaxf(t, 0.f);
+            else if (p.relu == 2) t = 0.5f * t * (1.f + erff(t * 0.70710678118654752f));
+            if (!p.add_first) t += ad[j];
+            v[j] = t;
           }
           if (p.y32) {
             float4* d4 = reinterpret_cast<float4*>(p.y32 + o_lane);
@@ -313,13 +326,55 @@ __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ in, __half* 
   if (ov) atomicOr(status, 1);
 }
 
+// rgb fp32 NCHW [B,3,H,W] -> fp16 hi/lo NHWC planes [B,H,W,32] (channels 3..31 zero): first ResNet conv input
+__global__ void rgb_to_planes32_kernel(const float* __restrict__ rgb, __half* __restrict__ hi, __half* __restrict__ lo,
+                                       int B, int HW, float scale, int* status) {
+  const size_t n = static_cast<size_t>(B) * HW;
+  bool ov = false;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n * 32;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i & 31);
+    const size_t px = i >> 5;
+    float v = 0.f;
+    if (c < 3) {
+      const size_t b = px / HW, p = px % HW;
+      v = rgb[(b * 3 + c) * HW + p] * scale;
+    }
+    ov |= fabsf(v) > 60000.f;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+  if (ov) atomicOr(status, 1);
+}
+
+// F.adaptive_avg_pool2d on fp32 NHWC: in [B,IH,IW,C] -> out [B,OH,OW,C]; window of output i = [floor(i*I/O), ceil((i+1)*I/O))
+__global__ void adaptive_avg_pool_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int IH, int IW,
+                                              int OH, int OW, int C) {
+  const size_t n = static_cast<size_t>(B) * OH * OW * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t px = i / C;
+    const int ox = static_cast<int>(px % OW), oy = static_cast<int>((px / OW) % OH), b = static_cast<int>(px / (static_cast<size_t>(OW) * OH));
+    const int ys = (oy * IH) / OH, ye = ((oy + 1) * IH + OH - 1) / OH;
+    const int xs = (ox * IW) / OW, xe = ((ox + 1) * IW + OW - 1) / OW;
+    float s = 0.f;
+    for (int y = ys; y < ye; ++y)
+      for (int x = xs; x < xe; ++x) s += in[((static_cast<size_t>(b) * IH + y) * IW + x) * C + c];
+    out[i] = s / static_cast<float>((ye - ys) * (xe - xs));
+  }
+}
+
 // w [COUT][CIN][kh][kw] (conv) -> scaled fp16 hi/lo [tap][COUT][CIN] with a per-output-channel factor folded in
 // (eval-BatchNorm scale).  transposed=1: w is ConvTranspose2d(k=2,s=2) [CIN][CO][2][2] and becomes a 1-tap
 // [4*CO][CIN] matrix, row n = (ky*2+kx)*CO + co.
+// cin_pad >= cin: output rows are cin_pad wide (extra input channels must be pre-zeroed by the caller)
 __global__ void pack_gen_weight_kernel(const float* __restrict__ w, const float* __restrict__ ch_scale,
                                        __half* __restrict__ hi, __half* __restrict__ lo, int cout, int cin, int taps,
-                                       int transposed, float scale) {
+                                       int transposed, float scale, int cin_pad = 0) {
   const int n = cout * cin * taps;
+  const int cp = cin_pad > 0 ? cin_pad : cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float v, f;
     size_t o;
@@ -327,7 +382,7 @@ __global__ void pack_gen_weight_kernel(const float* __restrict__ w, const float*
       const int tap = i % taps, ci = (i / taps) % cin, co = i / (taps * cin);
       v = w[i];
       f = ch_scale ? ch_scale[co] : 1.f;
-      o = (static_cast<size_t>(tap) * cout + co) * cin + ci;
+      o = (static_cast<size_t>(tap) * cout + co) * cp + ci;
     } else {
       const int co4 = cout / 4;  // here cout = 4*CO, taps == 1, n = cin*CO*4
       const int kk = i % 4, co = (i / 4) % co4, ci = i / (4 * co4);

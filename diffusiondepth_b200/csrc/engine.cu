@@ -66,6 +66,19 @@ int make_act_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C,
   if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
   return DD_OK;
 }
+// activations sampled with a spatial stride (stride-2 convs): elementStrides = {1, s, s, 1}; the box spans 16*s x 8*s
+// input positions and still delivers 16 x 8 pixels
+int make_act_map_strided(CUtensorMap* m, const __half* base, int B, int H, int W, int C, int bk, int stride) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(dd::TILE_W * stride), (cuuint32_t)(dd::TILE_H * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(strided activation) failed: " + std::to_string((int)r));
+  return DD_OK;
+}
 // activation strip for the halo kernel: box = {bk, 8, 18, 1}
 int make_strip_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C, int bk) {
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -149,8 +162,12 @@ cudaError_t configure_all_kernels() {
   if ((e = configure_umma_all_epi<64, 16, 64>()) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 dd::GenCfg<256>::SMEM_BYTES)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dd::convgen_umma_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              dd::GenCfg<192>::SMEM_BYTES);
+  if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::GenCfg<192>::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::GenCfg<128>::SMEM_BYTES)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dd::convgen_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              dd::GenCfg<64>::SMEM_BYTES);
 }
 
 template <int CIN, int COUT, int BK, int EPI>
@@ -249,6 +266,7 @@ struct Raw {
 // One producer convolution (neck / FPN): eval-BN folded into the weights (scale) and `shift`.
 struct GenLayer {
   int cin = 0, cout = 0, taps = 1, nt = 256, relu = 1, shuffle = 0;
+  int stride = 1, add_first = 0;
   __half* w_hi = nullptr;
   __half* w_lo = nullptr;
   float* shift = nullptr;
@@ -297,6 +315,21 @@ struct Producers {
   Planes F[4], L[4], P[4], O[4], XP[4];
   float* X[4] = {nullptr, nullptr, nullptr, nullptr};   // fp32 NHWC FPN outputs (X[0] aliases the loop's cond)
   float* UP[3] = {nullptr, nullptr, nullptr};           // fp32 NHWC upsampled maps at level i
+  bool resample = false;                                // pyramid is not exactly 2x: adaptive_avg_pool2d is a real resample
+  float* UPR[3] = {nullptr, nullptr, nullptr};          // raw ConvT output [B, 2H[i+1], 2W[i+1], 256] before pooling to level i
+};
+struct ResBlockW {
+  GenLayer c1, c2, ds;
+  bool has_ds = false;
+};
+struct ResNetW {
+  bool enabled = false, ready = false;
+  int H = 0, W = 0;
+  int depths[4] = {0, 0, 0, 0}, C[4] = {64, 128, 256, 512}, Hs[4] = {0, 0, 0, 0}, Ws[4] = {0, 0, 0, 0};
+  std::vector<ResBlockW> blocks[4];
+  Planes IN, T, Yp[2];
+  float* Y32[2] = {nullptr, nullptr};
+  float* D32 = nullptr;
 };
 
 }  // namespace
@@ -328,6 +361,7 @@ struct dd_engine {
   // graph
   Producers prod;
   Backbone bb;
+  ResNetW rn;
   bool feats_ready = false;  // dd_run_backbone has filled the neck's input planes
   bool cond_ready = false;  // dd_build_condition has filled `cond` for the next dd_denoise_decode(cond = NULL)
   cudaGraphExec_t graph_exec = nullptr;
@@ -414,8 +448,27 @@ size_t carve(dd_engine* e, void* base) {
       }
       planes(pv->XP[i], 256);
       pv->X[i] = (i == 0) ? v->cond : c.take<float>(px * 256);
-      if (i < pc.nlev - 1) pv->UP[i] = c.take<float>(px * 256);
+      if (i < pc.nlev - 1) {
+        pv->UP[i] = c.take<float>(px * 256);
+        if (pc.resample) pv->UPR[i] = c.take<float>(static_cast<size_t>(g.B) * 4 * pc.H[i + 1] * pc.W[i + 1] * 256);
+      }
     }
+  }
+  if (e->rn.enabled) {
+    const ResNetW& rc = e->rn;
+    ResNetW* rv = &v->rn;
+    const size_t pin = static_cast<size_t>(g.B) * rc.H * rc.W;
+    const size_t p0 = static_cast<size_t>(g.B) * rc.Hs[0] * rc.Ws[0] * 64;  // largest stage tensor (elements)
+    rv->IN.hi = c.take<__half>(pin * 32);
+    rv->IN.lo = c.take<__half>(pin * 32);
+    rv->T.hi = c.take<__half>(p0);
+    rv->T.lo = c.take<__half>(p0);
+    for (int k = 0; k < 2; ++k) {
+      rv->Yp[k].hi = c.take<__half>(p0);
+      rv->Yp[k].lo = c.take<__half>(p0);
+      rv->Y32[k] = c.take<float>(p0);
+    }
+    rv->D32 = c.take<float>(p0);
   }
   if (e->bb.enabled) {
     const Backbone& bc = e->bb;
@@ -791,31 +844,45 @@ int bn_fold(dd_engine* e, const std::string& bn, int ch, std::vector<float>& sca
   return DD_OK;
 }
 
-// conv weight key `wkey` ([cout][cin][k][k], or ConvT [cin][co][2][2] when transposed) + BN `bnkey`
+// conv weight key `wkey` ([cout][cin][k][k], or ConvT [cin][co][2][2] when transposed) followed by eval-BN `bnkey`
+// (folded), or — bnkey empty — by the plain bias `biaskey`.  cin_pad >= cin zero-pads the input-channel axis (RGB -> 32).
 int pack_gen(dd_engine* e, GenLayer& L, const std::string& wkey, const std::string& bnkey, int cin, int cout_conv,
-             int taps, bool transposed, cudaStream_t st, float* scratch) {
+             int taps, bool transposed, cudaStream_t st, float* scratch, int cin_pad = 0,
+             const std::string& biaskey = std::string()) {
   const Raw* w = find(e, wkey);
   if (!w) return fail(DD_ERR_INVALID, "missing weights: " + wkey);
   const int k = taps == 9 ? 3 : (transposed ? 2 : 1);
   std::vector<int64_t> want = transposed ? std::vector<int64_t>{cin, cout_conv, 2, 2}
                                          : std::vector<int64_t>{cout_conv, cin, k, k};
   if (w->shape != want) return fail(DD_ERR_INVALID, "weight shape mismatch: " + wkey);
-  std::vector<float> scale, shift;
+  std::vector<float> scale(cout_conv, 1.f), shift(cout_conv, 0.f);
   int rc;
-  if ((rc = bn_fold(e, bnkey, cout_conv, scale, shift, st))) return rc;
-  L.cin = cin;
+  if (!bnkey.empty()) {
+    if ((rc = bn_fold(e, bnkey, cout_conv, scale, shift, st))) return rc;
+  } else if (!biaskey.empty()) {
+    const Raw* b = find(e, biaskey);
+    if (!b) return fail(DD_ERR_INVALID, "missing weights: " + biaskey);
+    CUDA_TRY(cudaMemcpyAsync(shift.data(), b->ptr, cout_conv * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  const int cp = cin_pad > 0 ? cin_pad : cin;
+  L.cin = cp;
   L.taps = transposed ? 1 : taps;
   L.cout = transposed ? 4 * cout_conv : cout_conv;
   L.shuffle = transposed ? 1 : 0;
   L.relu = 1;
-  L.nt = (L.cout % 256 == 0) ? 256 : 192;
-  if (L.cout % L.nt != 0 || cin % 32 != 0) return fail(DD_ERR_UNSUPPORTED, "producer conv channels not tileable: " + wkey);
-  const size_t n = static_cast<size_t>(L.cout) * cin * L.taps;
+  L.nt = (L.cout % 256 == 0) ? 256 : (L.cout % 192 == 0 ? 192 : (L.cout % 128 == 0 ? 128 : 64));
+  if (L.cout % L.nt != 0 || cp % 32 != 0) return fail(DD_ERR_UNSUPPORTED, "producer conv channels not tileable: " + wkey);
+  const size_t n = static_cast<size_t>(L.cout) * cp * L.taps;
   float *d_scale = nullptr;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_hi), n * 2))) return rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_lo), n * 2))) return rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.shift), L.cout * 4))) return rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&d_scale), cout_conv * 4))) return rc;
+  if (cp != cin) {
+    CUDA_TRY(cudaMemsetAsync(L.w_hi, 0, n * 2, st));
+    CUDA_TRY(cudaMemsetAsync(L.w_lo, 0, n * 2, st));
+  }
   CUDA_TRY(cudaMemcpyAsync(d_scale, scale.data(), cout_conv * 4, cudaMemcpyHostToDevice, st));
   std::vector<float> shift_full(L.cout);
   for (int i = 0; i < L.cout; ++i) shift_full[i] = shift[i % cout_conv];
@@ -827,11 +894,11 @@ int pack_gen(dd_engine* e, GenLayer& L, const std::string& wkey, const std::stri
   CUDA_TRY(cudaStreamSynchronize(st));
   L.wscale = (amax > 0.f && isfinite(amax)) ? exp2f(floorf(log2f(32768.f / amax)) - 1.f) : 1.f;
   dd::pack_gen_weight_kernel<<<256, 256, 0, st>>>(w->ptr, d_scale, L.w_hi, L.w_lo, L.cout, cin, L.taps,
-                                                  transposed ? 1 : 0, L.wscale);
+                                                  transposed ? 1 : 0, L.wscale, cp);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(st));
-  if ((rc = make_wgen_map(&L.mb_hi, L.w_hi, L.cout, cin, L.taps, L.nt))) return rc;
-  if ((rc = make_wgen_map(&L.mb_lo, L.w_lo, L.cout, cin, L.taps, L.nt))) return rc;
+  if ((rc = make_wgen_map(&L.mb_hi, L.w_hi, L.cout, cp, L.taps, L.nt))) return rc;
+  if ((rc = make_wgen_map(&L.mb_lo, L.w_lo, L.cout, cp, L.taps, L.nt))) return rc;
   return DD_OK;
 }
 
@@ -859,8 +926,24 @@ int pack_producers(dd_engine* e, cudaStream_t st, float* scratch) {
   return DD_OK;
 }
 
+template <int NT>
+void launch_gen(int grid, cudaStream_t st, const CUtensorMap& m0h, const CUtensorMap& m0l, const CUtensorMap& m1h,
+                const CUtensorMap& m1l, const CUtensorMap& bh, const CUtensorMap& bl, const dd::GenConvArgs& a) {
+  dd::convgen_umma_kernel<NT><<<grid, 384, dd::GenCfg<NT>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, bh, bl, a);
+}
+void launch_gen_nt(int nt, int grid, cudaStream_t st, const CUtensorMap& m0h, const CUtensorMap& m0l, const CUtensorMap& m1h,
+                   const CUtensorMap& m1l, const CUtensorMap& bh, const CUtensorMap& bl, const dd::GenConvArgs& a) {
+  switch (nt) {
+    case 256: launch_gen<256>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a); break;
+    case 192: launch_gen<192>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a); break;
+    case 128: launch_gen<128>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a); break;
+    default: launch_gen<64>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a); break;
+  }
+}
+
+// H, W: OUTPUT grid.  With L.stride == 2 the sources live on a (src_h, src_w) grid.
 int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Planes& a1, int c1, int H, int W,
-            float* y32, const float* add32, const Planes* out, cudaStream_t st) {
+            float* y32, const float* add32, const Planes* out, cudaStream_t st, int src_h = 0, int src_w = 0) {
   const int B = e->cfg.batch;
   dd::GenConvArgs a;
   a.B = B;
@@ -878,6 +961,8 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   a.acc_scale = 1.f / (kProdScale * L.wscale);
   a.relu = L.relu;
   a.m_valid = 0;
+  a.stride = L.stride;
+  a.add_first = L.add_first;
   a.shuffle = L.shuffle;
   a.y32 = y32;
   a.add32 = add32;
@@ -888,8 +973,13 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   if (c0 + c1 != L.cin) return fail(DD_ERR_INVALID, "producer conv: source channels do not match the layer");
   CUtensorMap m0h, m0l, m1h, m1l;
   int rc;
-  if ((rc = make_act_map(&m0h, a0.hi, B, H, W, c0, 32))) return rc;
-  if ((rc = make_act_map(&m0l, a0.lo, B, H, W, c0, 32))) return rc;
+  if (L.stride == 1) {
+    if ((rc = make_act_map(&m0h, a0.hi, B, H, W, c0, 32))) return rc;
+    if ((rc = make_act_map(&m0l, a0.lo, B, H, W, c0, 32))) return rc;
+  } else {
+    if ((rc = make_act_map_strided(&m0h, a0.hi, B, src_h, src_w, c0, 32, L.stride))) return rc;
+    if ((rc = make_act_map_strided(&m0l, a0.lo, B, src_h, src_w, c0, 32, L.stride))) return rc;
+  }
   if (c1 > 0) {
     if ((rc = make_act_map(&m1h, a1.hi, B, H, W, c1, 32))) return rc;
     if ((rc = make_act_map(&m1l, a1.lo, B, H, W, c1, 32))) return rc;
@@ -899,16 +989,92 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   }
   const int work = a.m_tiles * a.n_tiles;
   const int grid = work < e->sm_count ? work : e->sm_count;
-  if (L.nt == 256)
-    dd::convgen_umma_kernel<256><<<grid, 384, dd::GenCfg<256>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
-  else
-    dd::convgen_umma_kernel<192><<<grid, 384, dd::GenCfg<192>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
+  launch_gen_nt(L.nt, grid, st, m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
   e->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("convgen launch: ") + cudaGetErrorString(err));
   return DD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ ResNet backbone
+// ResNetForMMBEV with BasicBlocks and no stem (reference src/model/backbone/mmbev_resnet.py:124-160; block = mmdet
+// BasicBlock): per stage, block 0 = conv3x3(s2)+BN+ReLU -> conv3x3+BN, skip = biased conv3x3(s2) without BN; other
+// blocks are stride 1 with identity skips.  Stride-2 convs use TMA element strides on the same tensor-core conv kernel.
+int pack_resnet(dd_engine* e, cudaStream_t st, float* scratch) {
+  ResNetW& r = e->rn;
+  int rc;
+  for (int s = 0; s < 4; ++s) {
+    r.blocks[s].assign(r.depths[s], ResBlockW());
+    const int cprev = s == 0 ? 3 : r.C[s - 1];
+    for (int b = 0; b < r.depths[s]; ++b) {
+      ResBlockW& W = r.blocks[s][b];
+      const std::string bp = "backbone.layers." + std::to_string(s) + "." + std::to_string(b) + ".";
+      const int cin = b == 0 ? cprev : r.C[s];
+      const int pad = (cin % 32) ? 32 : 0;
+      if ((rc = pack_gen(e, W.c1, bp + "conv1.weight", bp + "bn1", cin, r.C[s], 9, false, st, scratch, pad))) return rc;
+      W.c1.stride = b == 0 ? 2 : 1;
+      if ((rc = pack_gen(e, W.c2, bp + "conv2.weight", bp + "bn2", r.C[s], r.C[s], 9, false, st, scratch))) return rc;
+      W.c2.add_first = 1;  // out = relu(bn2(conv2) + skip)
+      W.has_ds = (b == 0);
+      if (W.has_ds) {
+        if ((rc = pack_gen(e, W.ds, bp + "downsample.weight", "", cin, r.C[s], 9, false, st, scratch, pad,
+                           bp + "downsample.bias"))) return rc;
+        W.ds.stride = 2;
+        W.ds.relu = 0;
+      }
+    }
+  }
+  r.ready = true;
+  return DD_OK;
+}
+
+int run_resnet(dd_engine* e, const float* rgb, float* const* feats_out, cudaStream_t st) {
+  ResNetW& r = e->rn;
+  const int B = e->cfg.batch;
+  {
+    const size_t n = static_cast<size_t>(B) * r.H * r.W * 32;
+    int blocks = static_cast<int>((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    dd::rgb_to_planes32_kernel<<<blocks, 256, 0, st>>>(rgb, r.IN.hi, r.IN.lo, B, r.H * r.W, kProdScale, e->status);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  const Planes none;
+  int rc;
+  Planes src = r.IN;
+  int src_c = 32, src_h = r.H, src_w = r.W;
+  for (int s = 0; s < 4; ++s) {
+    const int C = r.C[s], H = r.Hs[s], W = r.Ws[s];
+    int cur = 0;
+    for (int b = 0; b < r.depths[s]; ++b) {
+      const ResBlockW& Wt = r.blocks[s][b];
+      const bool last = (b == r.depths[s] - 1);
+      const int k = b & 1;
+      const Planes& in = (b == 0) ? src : r.Yp[cur];
+      const int in_c = (b == 0) ? src_c : C;
+      if ((rc = run_gen(e, Wt.c1, in, in_c, none, 0, H, W, nullptr, nullptr, &r.T, st, src_h, src_w))) return rc;
+      const float* skip;
+      if (Wt.has_ds) {
+        if ((rc = run_gen(e, Wt.ds, in, in_c, none, 0, H, W, r.D32, nullptr, nullptr, st, src_h, src_w))) return rc;
+        skip = r.D32;
+      } else {
+        skip = r.Y32[cur];
+      }
+      const Planes& outp = last ? e->prod.F[s] : r.Yp[k];
+      if ((rc = run_gen(e, Wt.c2, r.T, C, none, 0, H, W, r.Y32[k], skip, &outp, st))) return rc;
+      cur = k;
+    }
+    if (feats_out && feats_out[s]) {
+      if ((rc = transpose_out(r.Y32[cur], feats_out[s], B, C, H * W, st))) return rc;
+      e->launches++;
+    }
+    src = e->prod.F[s];
+    src_c = C;
+    src_h = H;
+    src_w = W;
+  }
+  return DD_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ Swin backbone
 constexpr float kTokScale = 16.f;  // fp16-split pre-scale of token activations (LayerNorm / GELU / attention outputs)
@@ -1030,6 +1196,8 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   a.acc_scale = 1.f / (kTokScale * G.wscale);
   a.relu = act;
   a.m_valid = M;
+  a.stride = 1;
+  a.add_first = 0;
   a.shuffle = 0;
   a.y32 = y32;
   a.add32 = add32;
@@ -1295,6 +1463,9 @@ int dd_finalize_weights(dd_handle h, void* cuda_stream) {
   h->bb.ready = false;
   if (h->bb.enabled)
     if ((rc = pack_backbone(h, st, scratch))) return rc;
+  h->rn.ready = false;
+  if (h->rn.enabled)
+    if ((rc = pack_resnet(h, st, scratch))) return rc;
   h->weights_ready = true;
   return DD_OK;
 }
@@ -1435,9 +1606,13 @@ int dd_enable_producers(dd_handle h, const dd_producer_config* pc) {
     p.W[i] = pc->widths[i];
     if (p.C[i] % 32 != 0 || p.C[i] <= 0) return fail(DD_ERR_UNSUPPORTED, "feature channels must be multiples of 32");
     if (p.neck && p.C[i] % 192 != 0) return fail(DD_ERR_UNSUPPORTED, "neck channel counts must tile by 192");
-    // the FPN's adaptive_avg_pool2d (reference head :121) is the identity only for exact 2x pyramids
-    if (i > 0 && (p.H[i - 1] != 2 * p.H[i] || p.W[i - 1] != 2 * p.W[i]))
-      return fail(DD_ERR_UNSUPPORTED, "native FPN needs an exact 2x pyramid (adaptive pooling would resample)");
+    // the FPN's adaptive_avg_pool2d (reference head :121) is the identity only for exact 2x pyramids; otherwise the
+    // ConvT output (2x the coarser level) is average-pooled down to the lateral's size by a dedicated kernel
+    if (i > 0 && (p.H[i - 1] != 2 * p.H[i] || p.W[i - 1] != 2 * p.W[i])) {
+      p.resample = true;
+      if (p.H[i - 1] > 2 * p.H[i] || p.W[i - 1] > 2 * p.W[i])
+        return fail(DD_ERR_UNSUPPORTED, "feature pyramid level is more than 2x its coarser neighbour");
+    }
   }
   if (p.H[0] != h->cfg.cond_h || p.W[0] != h->cfg.cond_w)
     return fail(DD_ERR_INVALID, "level-0 feature size must equal the condition map size");
@@ -1496,8 +1671,19 @@ int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, 
     const float* add = (i < p.nlev - 1) ? p.UP[i] : nullptr;
     if ((rc = run_gen(h, p.fl[i], p.O[i], p.C[i], none, 0, p.H[i], p.W[i], p.X[i], add, i > 0 ? &p.XP[i] : nullptr, st)))
       return rc;
-    if (i > 0)
-      if ((rc = run_gen(h, p.fu[i - 1], p.XP[i], 256, none, 0, p.H[i], p.W[i], p.UP[i - 1], nullptr, nullptr, st))) return rc;
+    if (i > 0) {
+      float* up_raw = p.resample ? p.UPR[i - 1] : p.UP[i - 1];
+      if ((rc = run_gen(h, p.fu[i - 1], p.XP[i], 256, none, 0, p.H[i], p.W[i], up_raw, nullptr, nullptr, st))) return rc;
+      if (p.resample) {  // F.adaptive_avg_pool2d(conv_up(pre_x), output_size = lateral size)  (reference head :121)
+        const size_t n = static_cast<size_t>(B) * p.H[i - 1] * p.W[i - 1] * 256;
+        int blocks = static_cast<int>((n + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        dd::adaptive_avg_pool_nhwc_kernel<<<blocks, 256, 0, st>>>(up_raw, p.UP[i - 1], B, 2 * p.H[i], 2 * p.W[i], p.H[i - 1],
+                                                                 p.W[i - 1], 256);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+      }
+    }
   }
   h->cond_ready = true;
   if (cond_out) {
@@ -1509,7 +1695,31 @@ int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, 
 
 int dd_enable_backbone(dd_handle h, const dd_backbone_config* bc) {
   if (!h || !bc) return fail(DD_ERR_INVALID, "null argument");
-  if (bc->kind != DD_BACKBONE_SWIN) return fail(DD_ERR_UNSUPPORTED, "only the Swin backbone runs natively");
+  if (bc->kind == DD_BACKBONE_RESNET) {
+    if (!h->prod.enabled || h->prod.neck || h->prod.nlev != 4)
+      return fail(DD_ERR_INVALID, "dd_enable_producers (4 levels, no neck) must be called first");
+    ResNetW r;
+    r.enabled = true;
+    r.H = bc->height;
+    r.W = bc->width;
+    int hh = bc->height, ww = bc->width;
+    for (int s = 0; s < 4; ++s) {
+      r.depths[s] = bc->depths[s];
+      if (r.depths[s] < 1) return fail(DD_ERR_INVALID, "bad ResNet depth");
+      hh = (hh - 1) / 2 + 1;  // 3x3, stride 2, pad 1
+      ww = (ww - 1) / 2 + 1;
+      r.Hs[s] = hh;
+      r.Ws[s] = ww;
+      if (hh != h->prod.H[s] || ww != h->prod.W[s] || r.C[s] != h->prod.C[s])
+        return fail(DD_ERR_INVALID, "backbone stage geometry does not match the producer pyramid");
+    }
+    h->rn = r;
+    h->bb.enabled = false;
+    h->weights_ready = false;
+    h->ws = nullptr;
+    return DD_OK;
+  }
+  if (bc->kind != DD_BACKBONE_SWIN) return fail(DD_ERR_UNSUPPORTED, "unknown backbone kind");
   if (!h->prod.enabled || !h->prod.neck || h->prod.nlev != 4)
     return fail(DD_ERR_INVALID, "dd_enable_producers (4 levels, has_neck) must be called first");
   if (bc->embed_dims != 192 || bc->window != 7)
@@ -1541,14 +1751,15 @@ int dd_enable_backbone(dd_handle h, const dd_backbone_config* bc) {
 int dd_run_backbone(dd_handle h, const float* rgb, float* const* feats_out, void* workspace, size_t workspace_bytes,
                     void* cuda_stream) {
   if (!h || !rgb) return fail(DD_ERR_INVALID, "null argument");
-  if (!h->bb.enabled || !h->weights_ready || !h->bb.ready) return fail(DD_ERR_INVALID, "backbone not enabled / weights not finalized");
+  const bool swin = h->bb.enabled && h->bb.ready, resnet = h->rn.enabled && h->rn.ready;
+  if (!h->weights_ready || !(swin || resnet)) return fail(DD_ERR_INVALID, "backbone not enabled / weights not finalized");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   int rc;
   if ((rc = bind_workspace(h, workspace, workspace_bytes))) return rc;
   CUDA_TRY(cudaMemsetAsync(h->status, 0, 64, st));
   h->launches = 0;
-  if ((rc = run_swin(h, rgb, feats_out, st))) return rc;
+  if ((rc = swin ? run_swin(h, rgb, feats_out, st) : run_resnet(h, rgb, feats_out, st))) return rc;
   h->feats_ready = true;
   return DD_OK;
 }

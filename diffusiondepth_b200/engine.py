@@ -108,10 +108,12 @@ class DenoiseEngine:
         self.producers = (tuple(channels), tuple(tuple(s_) for s_ in sizes), bool(has_neck))
         self._ws = None
 
-    def enable_backbone(self, image_hw, embed_dims=192, depths=(2, 2, 18, 2), num_heads=(6, 12, 24, 48), window=7):
-        """Run the Swin backbone natively as well (after enable_producers, before load_weights)."""
+    def enable_backbone(self, image_hw, embed_dims=192, depths=(2, 2, 18, 2), num_heads=(6, 12, 24, 48), window=7,
+                        kind="swin"):
+        """Run the backbone natively as well (after enable_producers, before load_weights).  kind: 'swin' (Swin-L) or
+        'resnet' (ResNetForMMBEV BasicBlock stages; only `depths` is used)."""
         bc = _cabi.DDBackboneConfig()
-        bc.kind, bc.embed_dims, bc.window = 1, int(embed_dims), int(window)
+        bc.kind, bc.embed_dims, bc.window = (1 if kind == "swin" else 2), int(embed_dims), int(window)
         bc.height, bc.width = int(image_hw[0]), int(image_hw[1])
         for i in range(4):
             bc.depths[i], bc.num_heads[i] = int(depths[i]), int(num_heads[i])

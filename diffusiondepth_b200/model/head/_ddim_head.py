@@ -118,12 +118,14 @@ class DDIMHeadBase(nn.Module):
         return sd
 
     @staticmethod
-    def _pyramid_ok(feats):
-        """Native FPN needs an exact 2x pyramid (adaptive_avg_pool2d == identity) and 32-multiple channels."""
-        for a, b in zip(feats[:-1], feats[1:]):
-            if a.shape[-2] != 2 * b.shape[-2] or a.shape[-1] != 2 * b.shape[-1]:
-                return False
-        return all(f.shape[1] % 32 == 0 for f in feats)
+    def _sizes_ok(sizes):
+        """Native FPN: each level at most 2x its coarser neighbour (== 2x: adaptive_avg_pool2d is the identity;
+        smaller, e.g. 57 vs 2*29: the engine's pooling kernel resamples)."""
+        return all(b[0] <= a[0] <= 2 * b[0] and b[1] <= a[1] <= 2 * b[1] for a, b in zip(sizes[:-1], sizes[1:]))
+
+    @classmethod
+    def _pyramid_ok(cls, feats):
+        return cls._sizes_ok([tuple(f.shape[-2:]) for f in feats]) and all(f.shape[1] % 32 == 0 for f in feats)
 
     def attach_backbone(self, backbone):
         self.__dict__['_backbone_ref'] = weakref.ref(backbone)
@@ -141,16 +143,36 @@ class DDIMHeadBase(nn.Module):
             h, w = (h + 1) // 2, (w + 1) // 2
         return sizes
 
+    @staticmethod
+    def resnet_pyramid(image_hw):
+        """Stage output sizes of the stem-less stride-2-per-stage ResNet (3x3, pad 1), finest first."""
+        h, w = image_hw
+        sizes = []
+        for _ in range(4):
+            h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            sizes.append((h, w))
+        return sizes
+
+    def backbone_pyramid(self, image_hw):
+        return self.swin_pyramid(image_hw) if self.variant == "swin" else self.resnet_pyramid(image_hw)
+
     def can_run_backbone(self, backbone, img) -> bool:
-        """Native Swin-L path: CUDA input, Swin-L architecture, exact 2x stage pyramid (needed by the native FPN)."""
-        if not (self.native_producers and self.native_backbone and self.variant == "swin" and img.is_cuda):
+        """Native backbone path: CUDA input and an architecture the engine instantiates — Swin-L for the Swin heads,
+        BasicBlock ResNetForMMBEV (64/128/256/512, stride 2 per stage) for the Res heads."""
+        if not (self.native_producers and self.native_backbone and img.is_cuda):
             return False
-        if type(backbone).__name__ != "SwinTransformer" or getattr(backbone, "num_features", None) != [192, 384, 768, 1536]:
-            return False
-        if [len(s.blocks) for s in backbone.stages] != [2, 2, 18, 2]:
-            return False
-        sizes = self.swin_pyramid(img.shape[-2:])
-        return all(a[0] == 2 * b[0] and a[1] == 2 * b[1] for a, b in zip(sizes[:-1], sizes[1:]))
+        name = type(backbone).__name__
+        if self.variant == "swin":
+            if name != "SwinTransformer" or getattr(backbone, "num_features", None) != [192, 384, 768, 1536]:
+                return False
+            if [len(s.blocks) for s in backbone.stages] != [2, 2, 18, 2]:
+                return False
+        else:
+            if name != "ResNetForMMBEV" or list(backbone.backbone_output_ids) != [0, 1, 2, 3]:
+                return False
+            if [st[0].conv2.out_channels for st in backbone.layers] != [64, 128, 256, 512]:
+                return False
+        return self._sizes_ok(self.backbone_pyramid(img.shape[-2:]))
 
     def _engine(self, batch, latent_hw, cond_hw, device, feats=None, image_hw=None) -> DenoiseEngine:
         """feats: backbone feature maps, or a (channels, sizes) pyramid spec -> native neck/FPN;
@@ -175,7 +197,10 @@ class DDIMHeadBase(nn.Module):
             if native:
                 eng.enable_producers(feats[0], feats[1], has_neck=self.variant == "swin")
             if image_hw is not None:
-                eng.enable_backbone(image_hw)
+                if self.variant == "swin":
+                    eng.enable_backbone(image_hw)
+                else:
+                    eng.enable_backbone(image_hw, depths=[len(st) for st in self._backbone().layers], kind="resnet")
             ts, cx, ce = self.scheduler.fused_coefficients(self.diffusion_inference_steps)
             eng.set_schedule(ts, cx, ce)
             self._engines[key] = eng
@@ -222,7 +247,7 @@ class DDIMHeadBase(nn.Module):
         with_backbone = fp is None
         if with_backbone:
             B, dev, dtype = image.shape[0], image.device, torch.float32
-            sizes = self.swin_pyramid(image.shape[-2:])
+            sizes = self.backbone_pyramid(image.shape[-2:])
             native = True
         else:
             if self.detach_fp is not False and self.detach_fp is not None:

@@ -133,7 +133,12 @@ int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, 
  * neck's input planes.  Requires dd_enable_producers(4 levels, has_neck = 1) with matching geometry; register the
  * reference keys of `depth_backbone.*` as "backbone.<key>" (the int64 `relative_position_index` buffers are not
  * needed).  Instantiated for Swin-L (embed_dims 192, head_dim 32, window 7). */
-enum dd_backbone_kind { DD_BACKBONE_SWIN = 1 };
+enum dd_backbone_kind {
+  DD_BACKBONE_SWIN = 1,   /* SwinTransformer (reference backbone/swin.py) */
+  DD_BACKBONE_RESNET = 2  /* ResNetForMMBEV with BasicBlocks, no stem (reference backbone/mmbev_resnet.py:124-187): depths[] =
+                             blocks per stage, channels 64/128/256/512, every stage stride 2; needs
+                             dd_enable_producers(4 levels, has_neck = 0); embed_dims / num_heads / window ignored */
+};
 typedef struct dd_backbone_config {
   int32_t kind;        /* enum dd_backbone_kind */
   int32_t embed_dims;  /* 192 */

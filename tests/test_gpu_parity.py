@@ -208,13 +208,50 @@ def test_native_swin_backbone_vs_oracle(hw):
                     p.copy_(saved[n])
 
 
-def test_native_producers_refuse_resampling_pyramids():
-    head = _res_head(2).to(DEV)
-    eng = dd.DenoiseEngine("res", 1, (29, 38), (29, 38), 2, DEV)
+@pytest.mark.parametrize("family,hw", [("res18", (228, 304)), ("res18", (70, 106)), ("res50", (64, 96))])
+def test_native_resnet_backbone_and_resampling_fpn_vs_oracle(family, hw):
+    """dd_run_backbone(kind = ResNet): stride-2 3x3 convs via TMA element strides, BN folded, residual add before
+    ReLU, biased strided skip convs — vs the fp64 restatement of reference mmbev_resnet.py:124-160; then the FPN on
+    the odd-sized pyramid (228x304 -> 114/57/29/15), where adaptive_avg_pool2d really resamples (head :121)."""
+    m = helpers.build_mirror(family, 2).to(DEV)
+    bb, head = m.depth_backbone, m.depth_head
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1)
+                mod.running_var.uniform_(0.7, 1.3)
+    try:
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        g = torch.Generator().manual_seed(31)
+        rgb = torch.randn(2, 3, *hw, generator=g)
+        depths = restate.RESNET_DEPTHS["mmbev_" + family]
+        ref = restate.resnet_backbone(sd, rgb.double(), depths)
+        sizes = head.resnet_pyramid(hw)
+        assert [tuple(r.shape[-2:]) for r in ref] == sizes
+        eng = head._engine(2, sizes[0], sizes[0], DEV, feats=([64, 128, 256, 512], sizes), image_hw=hw)
+        feats = eng.run_backbone(rgb.to(DEV), want_feats=True)
+        eng.poll_status()
+        for s, (f, r) in enumerate(zip(feats, ref)):
+            err = (f.double().cpu() - r).abs().max().item() / r.abs().max().item()
+            assert err < 5e-5, (s, err)
+        cond = eng.build_condition(None, want_cond=True)
+        cref = restate.fpn_condition(sd, ref)
+        err = (cond.double().cpu() - cref).abs().max().item() / cref.abs().max().item()
+        assert err < 5e-5, err
+    finally:
+        with torch.no_grad():
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.BatchNorm2d):
+                    mod.running_mean.zero_()
+                    mod.running_var.fill_(1.0)
+
+
+def test_producers_reject_unsupported_pyramids():
+    eng = dd.DenoiseEngine("res", 1, (32, 48), (32, 48), 2, DEV)
     with pytest.raises(dd.EngineError, match="DD_ERR_UNSUPPORTED"):
-        eng.enable_producers([64, 128, 256, 512], [(29, 38), (15, 19), (8, 10), (4, 5)], has_neck=False)
-    fp = [torch.randn(1, c, h, w, device=DEV) for c, (h, w) in zip((64, 128, 256, 512), ((29, 38), (15, 19), (8, 10), (4, 5)))]
-    assert not head._pyramid_ok(fp)  # the head then keeps the FPN on torch ops (adaptive pooling resamples)
+        eng.enable_producers([64, 128, 256, 512], [(32, 48), (10, 19), (5, 10), (3, 5)], has_neck=False)  # > 2x jump
+    with pytest.raises(dd.EngineError, match="DD_ERR_UNSUPPORTED"):
+        eng.enable_producers([60, 128, 256, 512], [(32, 48), (16, 24), (8, 12), (4, 6)], has_neck=False)  # 60 % 32 != 0
 
 
 # ------------------------------------------------------------------------------------------------ whole plugin
