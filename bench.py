@@ -6,7 +6,7 @@
 
 A "step" is one forward of the per-GPU batch (BASELINE config 3: 4 images, 352x1216, Swin-L, T=20) through the
 plugin (`Diffusion_DCbase_Model.forward`): Swin-L backbone + HAHI neck + FPN + T-step DDIM loop + decoder, all
-inside the CUDA engine (the tiny depth encoder `t()` is the only torch op left); for N > 1 the batch shards by rank (weak scaling: 4 images/GPU = BASELINE config 4
+inside the CUDA engine (no torch compute op is left on the path); for N > 1 the batch shards by rank (weak scaling: 4 images/GPU = BASELINE config 4
 at N = 8) and each step ends with the single all-gather of the depth maps.
 """
 import argparse

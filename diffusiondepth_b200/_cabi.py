@@ -54,6 +54,7 @@ SIGNATURES = {
     "dd_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "dd_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dd_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dd_last_launch_count": (C.c_int64, [C.c_void_p]),
     "dd_poll_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dd_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

@@ -348,6 +348,7 @@ struct dd_engine {
   float* dec_bt = nullptr;  // [16]
   float* dec_wc = nullptr;  // [9][16]
   float dec_bc = 0.f;
+  float *enc_w1 = nullptr, *enc_b1 = nullptr, *enc_w2 = nullptr, *enc_b2 = nullptr;  // folded encoder (optional)
   std::vector<void*> owned;
   // schedule
   std::vector<int64_t> ts;
@@ -1366,7 +1367,8 @@ int dd_set_weight(dd_handle h, const char* name, const float* dev_ptr, const int
   if (!h || !name || !dev_ptr || ndim < 0 || ndim > 4) return fail(DD_ERR_INVALID, "bad argument");
   bool known = strncmp(name, "hahineck.", 9) == 0 || strncmp(name, "conv_lateral.", 13) == 0 ||
                strncmp(name, "conv_up.", 8) == 0 ||  // step-invariant producers (optional, dd_enable_producers)
-               strncmp(name, "backbone.", 9) == 0;    // native Swin backbone (optional, dd_enable_backbone)
+               strncmp(name, "backbone.", 9) == 0 ||  // native backbone (optional, dd_enable_backbone)
+               strncmp(name, "depth_transform.conv_transform.", 31) == 0;  // encoder t() (optional, dd_encode)
   for (const char* k : kKeys) known |= (strcmp(k, name) == 0);
   if (!known) return fail(DD_ERR_INVALID, std::string("unknown weight key: ") + name);
   Raw r;
@@ -1457,6 +1459,35 @@ int dd_finalize_weights(dd_handle h, void* cuda_stream) {
   CUDA_TRY(cudaMemcpyAsync(h->dec_wc, wc_f.data(), wc_f.size() * 4, cudaMemcpyHostToDevice, st));
   h->dec_bc = bc[0];
   CUDA_TRY(cudaStreamSynchronize(st));
+  h->enc_w1 = nullptr;
+  if (find(h, "depth_transform.conv_transform.0.0.weight")) {
+    const std::string P = "depth_transform.conv_transform.";
+    const Raw *w1 = find(h, P + "0.0.weight"), *w2 = find(h, P + "1.0.weight");
+    if (!w2 || w1->shape != std::vector<int64_t>{16, 1, 3, 3} || w2->shape != std::vector<int64_t>{16, 16, 3, 3})
+      return fail(DD_ERR_INVALID, "encoder weights missing / wrong shape");
+    std::vector<float> s1, t1, s2, t2, hw1(144), hw2(2304);
+    if ((rc = bn_fold(h, P + "0.1", 16, s1, t1, st))) return rc;
+    if ((rc = bn_fold(h, P + "1.1", 16, s2, t2, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(hw1.data(), w1->ptr, 144 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hw2.data(), w2->ptr, 2304 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<float> f1(144), f2(2304);
+    for (int co = 0; co < 16; ++co)
+      for (int tap = 0; tap < 9; ++tap) f1[tap * 16 + co] = static_cast<float>(static_cast<double>(hw1[co * 9 + tap]) * s1[co]);
+    for (int co = 0; co < 16; ++co)
+      for (int ci = 0; ci < 16; ++ci)
+        for (int tap = 0; tap < 9; ++tap)
+          f2[(tap * 16 + ci) * 16 + co] = static_cast<float>(static_cast<double>(hw2[(co * 16 + ci) * 9 + tap]) * s2[co]);
+    if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->enc_w1), 144 * 4))) return rc;
+    if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->enc_b1), 64))) return rc;
+    if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->enc_w2), 2304 * 4))) return rc;
+    if ((rc = dev_alloc(h, reinterpret_cast<void**>(&h->enc_b2), 64))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->enc_w1, f1.data(), 144 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->enc_b1, t1.data(), 64, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->enc_w2, f2.data(), 2304 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->enc_b2, t2.data(), 64, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   h->prod.ready = false;
   if (h->prod.enabled)
     if ((rc = pack_producers(h, st, scratch))) return rc;
@@ -1822,6 +1853,31 @@ int dd_bench_gemm(dd_handle h, int32_t M, int32_t K, int32_t N, int32_t mode, in
   cudaEventDestroy(e1);
   for (void* p : {(void*)A.hi, (void*)A.lo, (void*)O.hi, (void*)O.lo, (void*)y, (void*)G.w_hi, (void*)G.w_lo, (void*)bias, (void*)status})
     cudaFree(p);
+  return DD_OK;
+}
+
+int dd_encode(dd_handle h, const float* depth, int32_t height, int32_t width, float* latent_out, void* cuda_stream) {
+  if (!h || !depth || !latent_out) return fail(DD_ERR_INVALID, "null argument");
+  if (!h->weights_ready || !h->enc_w1) return fail(DD_ERR_INVALID, "encoder weights (depth_transform.conv_transform.*) not registered");
+  if ((height + 1) / 2 != h->cfg.latent_h || (width + 1) / 2 != h->cfg.latent_w)
+    return fail(DD_ERR_INVALID, "depth map size does not match the engine's latent grid");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  dd::EncoderArgs a;
+  a.depth = depth;
+  a.w1 = h->enc_w1;
+  a.b1 = h->enc_b1;
+  a.w2 = h->enc_w2;
+  a.b2 = h->enc_b2;
+  a.out = latent_out;
+  a.H = height;
+  a.W = width;
+  a.h = h->cfg.latent_h;
+  a.w = h->cfg.latent_w;
+  dim3 grid((a.w + 15) / 16, (a.h + 15) / 16, h->cfg.batch);
+  dd::encoder_kernel<<<grid, 256, 0, st>>>(a);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("encoder: ") + cudaGetErrorString(err));
   return DD_OK;
 }
 

@@ -571,4 +571,79 @@ __global__ void __launch_bounds__(256) decoder_kernel(const DecoderArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ depth-latent encoder (t), fully fused
+// Conv2d(1,16,3,s2,p1, no bias) + BN(eval, folded) + LeakyReLU(0.2) -> Conv2d(16,16,3,1,1, no bias) + BN(folded) -> tanh
+// (reference src/model/ops/depth_transform.py:15-19,29-31; conv_bn_relu = src/model/common.py:45-60).
+// One block = 16 x 16 latent pixels; the 18 x 18 x 16 intermediate stays in shared memory.  Output NCHW [B,16,h,w]
+// (the head only returns it as `pred_init` / `gt_map_t`).
+struct EncoderArgs {
+  const float* depth;  // [B,1,H,W]
+  const float* w1;     // [9][16]      folded (tap, co)
+  const float* b1;     // [16]
+  const float* w2;     // [9][16][16]  folded (tap, ci, co)
+  const float* b2;     // [16]
+  float* out;          // [B,16,h,w]
+  int H, W, h, w;
+};
+__global__ void __launch_bounds__(256) encoder_kernel(const EncoderArgs a) {
+  constexpr int T = 16, M = T + 2, D = 2 * M + 1;  // mid tile 18x18, depth tile 37x37
+  __shared__ float s_d[D * D];
+  __shared__ float s_mid[M * M][17];
+  __shared__ float s_w1[9 * 16], s_b1[16], s_w2[9 * 16 * 16], s_b2[16];
+  const int b = blockIdx.z, y0 = blockIdx.y * T, x0 = blockIdx.x * T;
+  for (int i = threadIdx.x; i < 9 * 16 * 16; i += 256) s_w2[i] = a.w2[i];
+  if (threadIdx.x < 144) s_w1[threadIdx.x] = a.w1[threadIdx.x];
+  if (threadIdx.x < 16) {
+    s_b1[threadIdx.x] = a.b1[threadIdx.x];
+    s_b2[threadIdx.x] = a.b2[threadIdx.x];
+  }
+  // mid pixel (my, mx) (latent coords y0-1+my) reads depth rows 2*(y0-1+my)-1 .. +1  -> depth origin 2*(y0-1)-1
+  const int dy0 = 2 * (y0 - 1) - 1, dx0 = 2 * (x0 - 1) - 1;
+  for (int i = threadIdx.x; i < D * D; i += 256) {
+    const int yy = dy0 + i / D, xx = dx0 + i % D;
+    s_d[i] = (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) ? a.depth[(static_cast<size_t>(b) * a.H + yy) * a.W + xx] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M * M * 4; i += 256) {
+    const int cq = i & 3, mp = i >> 2;
+    const int my = mp / M, mx = mp % M;
+    const int ly = y0 - 1 + my, lx = x0 - 1 + mx;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ly >= 0 && ly < a.h && lx >= 0 && lx < a.w) {  // zero padding of the second conv outside the latent grid
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = s_b1[cq * 4 + j];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float v = s_d[(2 * my + tap / 3) * D + 2 * mx + tap % 3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fmaf(v, s_w1[tap * 16 + cq * 4 + j], o[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.2f * o[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_mid[mp][cq * 4 + j] = o[j];
+  }
+  __syncthreads();
+  const int py = threadIdx.x / T, px = threadIdx.x % T;
+  const int ly = y0 + py, lx = x0 + px;
+  if (ly >= a.h || lx >= a.w) return;
+  float acc[16];
+#pragma unroll
+  for (int co = 0; co < 16; ++co) acc[co] = s_b2[co];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const float* mp = s_mid[(py + tap / 3) * M + px + tap % 3];
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) {
+      const float v = mp[ci];
+#pragma unroll
+      for (int co = 0; co < 16; ++co) acc[co] = fmaf(v, s_w2[(tap * 16 + ci) * 16 + co], acc[co]);
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 16; ++co)
+    a.out[((static_cast<size_t>(b) * 16 + co) * a.h + ly) * a.w + lx] = tanhf(acc[co]);
+}
+
 }  // namespace dd

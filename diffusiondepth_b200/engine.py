@@ -18,6 +18,12 @@ DENOISER_KEYS = (
     "model.pred.3.weight", "model.pred.3.bias", "model.pred.4.weight", "model.pred.4.bias")
 FUSE_KEYS = ("model.upsample_fuse.convA.conv.weight", "model.upsample_fuse.convA.conv.bias",
              "model.upsample_fuse.convB.conv.weight", "model.upsample_fuse.convB.conv.bias")
+ENCODER_KEYS = (
+    "depth_transform.conv_transform.0.0.weight", "depth_transform.conv_transform.0.1.weight",
+    "depth_transform.conv_transform.0.1.bias", "depth_transform.conv_transform.0.1.running_mean",
+    "depth_transform.conv_transform.0.1.running_var", "depth_transform.conv_transform.1.0.weight",
+    "depth_transform.conv_transform.1.1.weight", "depth_transform.conv_transform.1.1.bias",
+    "depth_transform.conv_transform.1.1.running_mean", "depth_transform.conv_transform.1.1.running_var")
 DECODER_KEYS = (
     "depth_transform.conv_inv_transform.0.weight", "depth_transform.conv_inv_transform.0.bias",
     "depth_transform.conv_inv_transform.1.weight", "depth_transform.conv_inv_transform.1.bias",
@@ -79,6 +85,8 @@ class DenoiseEngine:
     # ---------------------------------------------------------------- setup
     def load_weights(self, tensors: Dict[str, torch.Tensor]):
         keys = DENOISER_KEYS + DECODER_KEYS + (FUSE_KEYS if self.variant == "swin" else ())
+        if all(k in tensors for k in ENCODER_KEYS):
+            keys = keys + ENCODER_KEYS
         if self.backbone is not None:
             keys = keys + tuple(k for k in tensors if k.startswith("backbone.") and tensors[k].is_floating_point())
         if self.producers is not None:
@@ -208,6 +216,16 @@ class DenoiseEngine:
             self._h, C.c_void_p(cond.data_ptr()), C.c_void_p(noisy.data_ptr()), (C.c_int64 * B)(*ts),
             C.c_void_p(eps.data_ptr()), C.c_void_p(self._aligned(ws)), ws.numel() - 1024, C.c_void_p(self._stream())))
         return eps
+
+    def encode(self, depth: torch.Tensor) -> torch.Tensor:
+        """latent = depth_transform.t(depth): [B,1,H,W] -> [B,16,ceil(H/2),ceil(W/2)]."""
+        B, (h, w) = self.batch, self.latent_hw
+        H, W = depth.shape[-2:]
+        self._check_in(depth, (B, 1, H, W))
+        out = torch.empty(B, 16, h, w, device=self.device, dtype=torch.float32)
+        _cabi.check(self.lib.dd_encode(self._h, C.c_void_p(depth.data_ptr()), H, W, C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(self._stream())))
+        return out
 
     def decode(self, latent: torch.Tensor, want_logits=False):
         B, (h, w) = self.batch, self.latent_hw

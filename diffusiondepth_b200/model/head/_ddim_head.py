@@ -13,7 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..._cabi import EngineError
-from ...engine import DECODER_KEYS, DENOISER_KEYS, FUSE_KEYS, DenoiseEngine
+from ...engine import DECODER_KEYS, DENOISER_KEYS, ENCODER_KEYS, FUSE_KEYS, DenoiseEngine
 from .._blocks import ConvModule, exact_fp32
 from ..diffusers.schedulers.scheduling_ddim import DDIMScheduler
 from ..ops import depth_transform as _codec  # noqa: F401  (registers the codec classes)
@@ -104,7 +104,7 @@ class DDIMHeadBase(nn.Module):
     # ------------------------------------------------------------------------------------------ engine bridge
     def _engine_tensors(self):
         sd = {}
-        for k in DENOISER_KEYS + DECODER_KEYS + (FUSE_KEYS if self.variant == "swin" else ()):
+        for k in DENOISER_KEYS + DECODER_KEYS + ENCODER_KEYS + (FUSE_KEYS if self.variant == "swin" else ()):
             mod, _, leaf = k.rpartition(".")
             obj = self.get_submodule(mod)
             sd[k] = getattr(obj, leaf)
@@ -256,11 +256,16 @@ class DDIMHeadBase(nn.Module):
             fp = [f.contiguous().float() for f in fp]
             B, dev, dtype = fp[0].shape[0], fp[0].device, fp[0].dtype
             native = self.native_producers and fp[0].is_cuda and self._pyramid_ok(fp)
-        with torch.no_grad(), exact_fp32():
-            gt_map_t = self.depth_transform.t(gt_depth_map)
-            cond = None if native else self._condition(self._neck(fp)).contiguous()
-        latent_hw = tuple(gt_map_t.shape[-2:])
-        x_T = self._draw_noise((B, *gt_map_t.shape[-3:]), dev, dtype, noise)
+        Hd, Wd = gt_depth_map.shape[-2:]
+        latent_hw = ((Hd + 1) // 2, (Wd + 1) // 2)  # shape of depth_transform.t(gt): conv3x3 stride 2 pad 1
+        gt_map_t = None
+        if not native:
+            with torch.no_grad(), exact_fp32():
+                gt_map_t = self.depth_transform.t(gt_depth_map)
+                cond = self._condition(self._neck(fp)).contiguous()
+        else:
+            cond = None
+        x_T = self._draw_noise((B, 16, *latent_hw), dev, dtype, noise)
         if native:  # (backbone +) neck + FPN + loop + decoder inside the engine; the condition map never leaves NHWC
             want_cond = self.capture_cond or self.training or self.eval_ddim_loss
             if with_backbone:
@@ -271,6 +276,7 @@ class DDIMHeadBase(nn.Module):
             else:
                 eng = self._engine(B, latent_hw, tuple(fp[0].shape[-2:]), dev, feats=fp)
                 cond = eng.build_condition(fp, want_cond=want_cond)
+            gt_map_t = eng.encode(gt_depth_map.contiguous().float())  # returned as pred_init / gt_map_t only
             refined_depth, refined_depth_t, logits = eng.denoise_decode(None, x_T, want_latent=True,
                                                                         want_logits=self.capture_logits)
         else:

@@ -172,6 +172,10 @@ int dd_denoiser_forward(dd_handle h, const float* cond, const float* noisy, cons
 int dd_decode(dd_handle h, const float* latent, float* logit_out, float* depth_out, void* workspace,
               size_t workspace_bytes, void* cuda_stream);
 
+/* latent = depth_transform.t(depth) (reference src/model/ops/depth_transform.py:29-31): depth [B,1,height,width] ->
+ * latent_out [B,16,ceil(height/2),ceil(width/2)].  Needs the optional keys `depth_transform.conv_transform.*`. */
+int dd_encode(dd_handle h, const float* depth, int32_t height, int32_t width, float* latent_out, void* cuda_stream);
+
 /* Synchronise `cuda_stream` and report DD_ERR_RANGE if any activation left the fp16 split's range since the
  * last hot-path call started (DD_OK otherwise).  The hot-path calls themselves never synchronise unless
  * DD_FLAG_CHECK_RANGE is set. */

@@ -99,6 +99,31 @@ def test_decoder_vs_oracle():
         assert (depth.cpu()[z.float() < -14.5] == 999999.0).all()  # clamp(1e-6) branch of inv_t
 
 
+@pytest.mark.parametrize("HW", [(38, 54), (37, 53), (352, 1216)])
+def test_encoder_vs_oracle(HW):
+    """dd_encode = depth_transform.t (reference depth_transform.py:15-19,29-31), odd sizes included."""
+    head = _res_head(2).to(DEV)
+    with torch.no_grad():
+        for m in head.depth_transform.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.3)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    sd = _head_sd(head)
+    g = torch.Generator().manual_seed(8)
+    depth = torch.rand(2, 1, *HW, generator=g) * 80
+    lat = ((HW[0] + 1) // 2, (HW[1] + 1) // 2)
+    eng = head._engine(2, lat, lat, DEV)
+    out = eng.encode(depth.to(DEV))
+    ref = restate.encode(sd, depth.double())
+    assert out.shape == ref.shape
+    assert (out.double().cpu() - ref).abs().max().item() < 2e-5
+    from diffusiondepth_b200.model._blocks import exact_fp32
+    with torch.no_grad(), exact_fp32():  # (cuDNN's default TF32 would itself be off by more than the tolerance)
+        assert torch.allclose(out, head.depth_transform.t(depth.to(DEV)), atol=2e-5)
+
+
 @pytest.mark.parametrize("variant,hw,T", [("res", (19, 27), 5), ("swin", (18, 26), 5), ("swin", (24, 40), 20)])
 def test_loop_and_decode_vs_oracle(variant, hw, T):
     """T-step DDIM loop + decoder through dd_denoise_decode vs the fp64 restatement; CUDA-graph replay and the
