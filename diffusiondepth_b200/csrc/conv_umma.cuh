@@ -44,6 +44,7 @@ struct ConvArgs {
   __half* out_lo;
   float split_scale;       // power-of-two scale applied before the fp16 split of the output
   int* status;             // bit0 set if an fp16 operand would overflow
+  int fp8_probe;           // timing probe only: issue the two correction products as FP8 MMAs (results are garbage)
 };
 
 template <int CIN, int COUT, int BK>

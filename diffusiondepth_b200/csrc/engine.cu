@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -508,6 +509,7 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
   a.out_lo = out_lo;
   a.split_scale = kActScale;
   a.status = e->status;
+  a.fp8_probe = getenv("DD_FP8_PROBE") ? 1 : 0;
   cudaError_t err = cudaSuccess;
   e->launches++;
   int which = -1;
@@ -1961,6 +1963,7 @@ int dd_conv3x3(dd_handle h, const float* x, const float* w, const float* b, floa
   a.out_lo = nullptr;
   a.split_scale = 1.f;
   a.status = status;
+  a.fp8_probe = 0;
   cudaError_t err = cudaSuccess;
   const ShapeInfo s = kShapes[sid];
   if (h->cfg.flags & DD_FLAG_SIMT_CONV) {
