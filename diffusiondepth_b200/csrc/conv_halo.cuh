@@ -20,7 +20,12 @@ namespace dd {
 constexpr int HALO_TH = 16;  // output tile: 16 rows x 8 columns = 128 pixels
 constexpr int HALO_TW = 8;
 
-template <int CIN, int COUT, int BK>
+// PAIR = true: two CTAs of one cluster (one TPC) run ONE tcgen05.mma.cta_group::2 with M = 256: each CTA stages its own
+// 128-pixel strips (A) and HALF of the weight tile (COUT/2 rows of B); the hardware feeds both tensor cores from the two
+// halves, so per SM the weight tile is written to and read from shared memory half as often.  Measured motivation
+// (profiles/README.md): the single-CTA kernel moves ~110 KB through each SM's shared-memory port per (chunk, tap) stage
+// = ~860 cycles at 128 B/clk, above the 768 cycles of tensor work -> it is shared-memory-port bound.
+template <int CIN, int COUT, int BK, bool PAIR = false>
 struct HaloCfg {
   static_assert(CIN % BK == 0 && (BK == 16 || BK == 32), "bad K chunk");
   static constexpr int KC = CIN / BK;
@@ -29,10 +34,11 @@ struct HaloCfg {
   static constexpr int STRIP_BYTES = STRIP_ROWS * ROW_BYTES;        // one plane, one dx
   static constexpr int STRIP_PAD = (STRIP_BYTES + 1023) / 1024 * 1024;
   static constexpr int A_SLOT = 6 * STRIP_PAD;                      // 3 dx x (hi, lo)
-  static constexpr int B_TILE = COUT * ROW_BYTES;                   // one plane, one tap, one chunk
+  static constexpr int B_ROWS = PAIR ? COUT / 2 : COUT;             // weight rows this CTA stages
+  static constexpr int B_TILE = B_ROWS * ROW_BYTES;                 // one plane, one tap, one chunk
   static constexpr int B_TILE_PAD = (B_TILE + 1023) / 1024 * 1024;
   static constexpr int B_SLOT = 2 * B_TILE_PAD;
-  static constexpr int A_SLOTS = 2;
+  static constexpr int A_SLOTS = PAIR ? 3 : 2;
   static constexpr int XPOSE_BYTES = 4 * 32 * 32 * 4;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - XPOSE_BYTES - A_SLOTS * A_SLOT;
   static constexpr int B_SLOTS_RAW = BUDGET / B_SLOT;
@@ -52,12 +58,13 @@ struct HaloCfg {
   static constexpr int GROUP_CH = COUT / 4;
 };
 
-template <int CIN, int COUT, int BK, int EPI>
+template <int CIN, int COUT, int BK, int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(256, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const ConvArgs p) {
-  using C = HaloCfg<CIN, COUT, BK>;
+  using C = HaloCfg<CIN, COUT, BK, PAIR>;
+  static_assert(!PAIR || C::NACC == 1, "pair mode is for the wide layers");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -75,32 +82,43 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // cluster dims (2,1,1): rank == blockIdx.x & 1
+  // Both CTAs of a pair walk the same number of tiles (tile = pair base + rank); a tile past the end is computed on
+  // zero-filled (out-of-bounds) strips and never stored.
+#define DD_TILE_LOOP for (int tile = blockIdx.x; (PAIR ? (tile & ~1) : tile) < p.num_tiles; tile += gridDim.x)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA_hi);
     tma_prefetch_desc(&tmA_lo);
     tma_prefetch_desc(&tmB_hi);
     tma_prefetch_desc(&tmB_lo);
+    // pair mode: the leader's full barriers take one arrive.expect_tx from each CTA's producer; its tempty barriers take
+    // the four epilogue warps of both CTAs; empty / tfull barriers live in each CTA and are hit by multicast commits
     for (int s = 0; s < C::A_SLOTS; ++s) {
-      mbar_init(&a_full[s], 1);
+      mbar_init(&a_full[s], PAIR ? 2 : 1);
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < C::B_SLOTS; ++s) {
-      mbar_init(&b_full[s], 1);
+      mbar_init(&b_full[s], PAIR ? 2 : 1);
       mbar_init(&b_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);
+      mbar_init(&tempty_bar[b], PAIR ? 8 : 4);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -108,17 +126,27 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     // ------------------------------------------------------------------ TMA producer (A strips)
     int sa = 0;
     uint32_t pa = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    DD_TILE_LOOP {
       const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
       const int x0 = tx * HALO_TW, y0 = ty * HALO_TH;
       for (int kc = 0; kc < C::KC; ++kc) {
         mbar_wait(&a_empty[sa], pa ^ 1);
         uint8_t* s = a_ring + sa * C::A_SLOT;
-        mbar_arrive_expect_tx(&a_full[sa], C::A_TX);
+        if constexpr (PAIR) {
+          const uint32_t lead = mapa_u32(smem_u32(&a_full[sa]), 0);
+          mbar_arrive_expect_tx_cluster(lead, C::A_TX);
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          tma_load_4d(s + (2 * dx) * C::STRIP_PAD, &tmA_hi, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
-          tma_load_4d(s + (2 * dx + 1) * C::STRIP_PAD, &tmA_lo, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
+          for (int dx = 0; dx < 3; ++dx) {
+            tma_load_4d_pair(s + (2 * dx) * C::STRIP_PAD, &tmA_hi, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+            tma_load_4d_pair(s + (2 * dx + 1) * C::STRIP_PAD, &tmA_lo, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+          }
+        } else {
+          mbar_arrive_expect_tx(&a_full[sa], C::A_TX);
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            tma_load_4d(s + (2 * dx) * C::STRIP_PAD, &tmA_hi, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
+            tma_load_4d(s + (2 * dx + 1) * C::STRIP_PAD, &tmA_lo, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
+          }
         }
         if (++sa == C::A_SLOTS) {
           sa = 0;
@@ -130,14 +158,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     // ------------------------------------------------------------------ TMA producer (B weight tiles)
     int sb = 0;
     uint32_t pb = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    DD_TILE_LOOP {
       for (int kc = 0; kc < C::KC; ++kc) {
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_empty[sb], pb ^ 1);
           uint8_t* s = b_ring + sb * C::B_SLOT;
-          mbar_arrive_expect_tx(&b_full[sb], C::B_TX);
-          tma_load_3d(s, &tmB_hi, &b_full[sb], kc * BK, 0, tap);
-          tma_load_3d(s + C::B_TILE_PAD, &tmB_lo, &b_full[sb], kc * BK, 0, tap);
+          if constexpr (PAIR) {  // this CTA's half of the output channels
+            const uint32_t lead = mapa_u32(smem_u32(&b_full[sb]), 0);
+            mbar_arrive_expect_tx_cluster(lead, C::B_TX);
+            tma_load_3d_pair(s, &tmB_hi, lead, kc * BK, static_cast<int>(rank) * C::B_ROWS, tap);
+            tma_load_3d_pair(s + C::B_TILE_PAD, &tmB_lo, lead, kc * BK, static_cast<int>(rank) * C::B_ROWS, tap);
+          } else {
+            mbar_arrive_expect_tx(&b_full[sb], C::B_TX);
+            tma_load_3d(s, &tmB_hi, &b_full[sb], kc * BK, 0, tap);
+            tma_load_3d(s + C::B_TILE_PAD, &tmB_lo, &b_full[sb], kc * BK, 0, tap);
+          }
           if (++sb == C::B_SLOTS) {
             sb = 0;
             pb ^= 1;
@@ -145,12 +180,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_f16(TILE_M, COUT);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
+    constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, COUT);
     int sa = 0, sb = 0, buf = 0;
     uint32_t pa = 0, pb = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    DD_TILE_LOOP {
       mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS);
@@ -166,7 +201,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint32_t sa_lo = sa_hi + C::STRIP_PAD;
           const uint32_t sb_hi = smem_u32(b_ring + sb * C::B_SLOT);
           const uint32_t sb_lo = sb_hi + C::B_TILE_PAD;
-          if (p.fp8_probe) {
+          if (!PAIR && p.fp8_probe) {
             // DESIGN probe (DD_FP8_PROBE=1): fp16 hi*hi (2 x K16) + the two correction products as ONE e4m3 MMA each
             // (K = 32): 4 instructions per chunk instead of 6.  Operand bytes are reinterpreted, results are garbage.
             constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) | (static_cast<uint32_t>(TILE_M >> 4) << 24);
@@ -188,20 +223,29 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               umma_f16(d_tmem, a_lo, b_hi, idesc, first);
               umma_f16(d_tmem + COUT, a_hi, b_lo, idesc, first);
               umma_f16(d_tmem + 2 * COUT, a_hi, b_hi, idesc, first);
+            } else if constexpr (PAIR) {
+              umma_f16_pair(d_tmem, a_lo, b_hi, idesc, first);
+              umma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1u);
             } else {
               umma_f16(d_tmem, a_lo, b_hi, idesc, first);
               umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
               umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
             }
           }
-          umma_commit(&b_empty[sb]);
+          if constexpr (PAIR) umma_commit_pair(&b_empty[sb], 3); else umma_commit(&b_empty[sb]);
           if (++sb == C::B_SLOTS) {
             sb = 0;
             pb ^= 1;
           }
         }
-        umma_commit(&a_empty[sa]);
-        if (kc == C::KC - 1) umma_commit(&tfull_bar[buf]);
+        if constexpr (PAIR) {
+          umma_commit_pair(&a_empty[sa], 3);
+          if (kc == C::KC - 1) umma_commit_pair(&tfull_bar[buf], 3);
+        } else {
+          umma_commit(&a_empty[sa]);
+          if (kc == C::KC - 1) umma_commit(&tfull_bar[buf]);
+        }
         if (++sa == C::A_SLOTS) {
           sa = 0;
           pa ^= 1;
@@ -218,10 +262,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     uint32_t full_phase = 0;
     int buf = 0, par = 0;
     float* T = xpose + q * 1024;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    long long clk0 = 0;
+    unsigned long long ns0 = 0;
+    const bool probe = p.clk_probe != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
+    if (probe) {
+      clk0 = clock64();
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    }
+    DD_TILE_LOOP {
       const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
       const int x = tx * HALO_TW + c, y = ty * HALO_TH + r;
-      const bool valid = (x < p.W) && (y < p.H);
+      const bool valid = (x < p.W) && (y < p.H) && (tile < p.num_tiles);
       const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       const uint32_t row_off = static_cast<uint32_t>(pix * COUT);
@@ -306,7 +357,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+        else mbar_arrive(&tempty_bar[buf]);
+      }
 
       if constexpr (EPI == EPI_F32_STATS) {
 #pragma unroll
@@ -324,7 +378,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int e = threadIdx.x - 128;
-        if (e < 8) {
+        if (e < 8 && tile < p.num_tiles) {
           const int g = e >> 1, which = e & 1;
           float t = 0.f;
 #pragma unroll
@@ -338,13 +392,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
       buf ^= 1;
     }
+    if (probe) {
+      unsigned long long ns1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+      atomicAdd(p.clk_probe, static_cast<unsigned long long>(clock64() - clk0));
+      atomicAdd(p.clk_probe + 1, ns1 - ns0);
+    }
   }
 
+#undef DD_TILE_LOOP
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 

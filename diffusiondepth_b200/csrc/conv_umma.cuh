@@ -45,6 +45,7 @@ struct ConvArgs {
   float split_scale;       // power-of-two scale applied before the fp16 split of the output
   int* status;             // bit0 set if an fp16 operand would overflow
   int fp8_probe;           // timing probe only: issue the two correction products as FP8 MMAs (results are garbage)
+  unsigned long long* clk_probe;  // timing probe only (nullable): CTA 0 adds {SM cycles, nanoseconds} of its lifetime
 };
 
 template <int CIN, int COUT, int BK>

@@ -105,10 +105,10 @@ int make_patch_map(CUtensorMap* m, const __half* base, int B, int H, int W, int 
   return DD_OK;
 }
 // weights: [9][COUT][CIN] fp16; box = {bk, COUT, 1}
-int make_w_map(CUtensorMap* m, const __half* base, int cout, int cin, int bk) {
+int make_w_map(CUtensorMap* m, const __half* base, int cout, int cin, int bk, int box_rows = 0) {
   cuuint64_t gdim[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
   cuuint64_t gstr[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
-  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)cout, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(box_rows ? box_rows : cout), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -187,6 +187,10 @@ constexpr int kSwapBK[5] = {16, 0, 0, 32, 32};    // K chunk of the swapped-oper
 // and stay on the classic kernel; row-halo reuse pays for the wide layers.
 constexpr bool kUseSwap[5] = {false, false, false, true, false};
 constexpr bool kUseHalo[5] = {false, true, true, false, false};
+// CTA pairs (cta_group::2) measured in cycles (profiles/clk_probe.py): 64->256 -6 % (its short K leaves the epilogue
+// exposed and halving the weight traffic through shared memory helps it), 256->256 +7 % (already at ~81 % tensor-pipe
+// occupancy = the cuBLAS level; the pair only adds cross-SM latency per instruction) -> pairs serve 64->256 only.
+constexpr bool kUsePair[5] = {false, true, false, false, false};
 template <int CIN, int COUT, int BK, int EPI>
 cudaError_t launch_swap(const CUtensorMap& p_hi, const CUtensorMap& p_lo, const CUtensorMap& w, const dd::ConvArgs& args,
                         int sm_count, cudaStream_t st) {
@@ -218,6 +222,37 @@ cudaError_t launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
   dd::conv3x3_halo_kernel<CIN, COUT, BK, EPI><<<grid, 256, C::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, args);
   return cudaGetLastError();
 }
+// CTA-pair variant (cluster of 2, tcgen05 cta_group::2) of the halo kernel for the 256-wide layers
+template <int CIN, int COUT, int BK, int EPI>
+cudaError_t launch_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                        const CUtensorMap& b_lo, const dd::ConvArgs& args, int sm_count, cudaStream_t st) {
+  using C = dd::HaloCfg<CIN, COUT, BK, true>;
+  int grid = ((args.num_tiles + 1) & ~1) < (sm_count & ~1) ? ((args.num_tiles + 1) & ~1) : (sm_count & ~1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, dd::conv3x3_halo_kernel<CIN, COUT, BK, EPI, true>, a_hi, a_lo, b_hi, b_lo, args);
+}
+template <int CIN, int COUT, int BK>
+cudaError_t configure_pair_all_epi() {
+  using C = dd::HaloCfg<CIN, COUT, BK, true>;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<CIN, COUT, BK, dd::EPI_F32_STATS, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<CIN, COUT, BK, dd::EPI_SPLIT, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dd::conv3x3_halo_kernel<CIN, COUT, BK, dd::EPI_F32, true>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+}
 template <int CIN, int COUT, int BK>
 cudaError_t configure_halo_all_epi() {
   using C = dd::HaloCfg<CIN, COUT, BK>;
@@ -231,6 +266,8 @@ cudaError_t configure_halo_all_epi() {
 }
 cudaError_t configure_halo_kernels() {
   cudaError_t e;
+  if ((e = configure_pair_all_epi<64, 256, 32>()) != cudaSuccess) return e;
+  if ((e = configure_pair_all_epi<256, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_halo_all_epi<16, 64, 16>()) != cudaSuccess) return e;
   if ((e = configure_halo_all_epi<64, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_halo_all_epi<256, 256, 32>()) != cudaSuccess) return e;
@@ -255,6 +292,7 @@ struct ConvLayer {
   float wscale = 1.f;
   CUtensorMap mb_hi, mb_lo;
   CUtensorMap mh_hi, mh_lo;  // same planes, box for the halo kernel's K chunk
+  CUtensorMap mp_hi, mp_lo;  // same, box of COUT/2 rows for the CTA-pair kernel (256-wide layers)
   __half* w_swap = nullptr;  // [9][128][CIN]: rows co = hi, 64+co = lo (swapped-operand kernel, narrow layers)
   CUtensorMap mw_swap;
 };
@@ -338,6 +376,7 @@ struct ResNetW {
 struct dd_engine {
   dd_config cfg;
   int sm_count = 0;
+  unsigned long long* clk_probe = nullptr;  // DD_CLK_PROBE=1: per-launch SM cycles / nanoseconds (dd_bench_conv)
   bool weights_ready = false;
   std::map<std::string, Raw> raw;
   // packed parameters (device memory owned by the engine)
@@ -510,6 +549,7 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
   a.split_scale = kActScale;
   a.status = e->status;
   a.fp8_probe = getenv("DD_FP8_PROBE") ? 1 : 0;
+  a.clk_probe = e->clk_probe;
   cudaError_t err = cudaSuccess;
   e->launches++;
   int which = -1;
@@ -572,6 +612,22 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
     const int hbk = kHaloBK[L.sid];
     if ((rc = make_strip_map(&ma_hi, in_hi, g.B, g.h, g.w, s.cin, hbk))) return rc;
     if ((rc = make_strip_map(&ma_lo, in_lo, g.B, g.h, g.w, s.cin, hbk))) return rc;
+    const bool use_pair = (e->cfg.flags & DD_FLAG_PAIR_WIDE) && kUsePair[L.sid];
+    if (use_pair) {
+#define PAIR_CASE(ID, CI, CO, BK)                                                                                   \
+  case ID:                                                                                                          \
+    err = (epi == dd::EPI_F32_STATS)                                                                                \
+              ? launch_pair<CI, CO, BK, dd::EPI_F32_STATS>(ma_hi, ma_lo, L.mp_hi, L.mp_lo, a, e->sm_count, st)      \
+          : (epi == dd::EPI_SPLIT)                                                                                  \
+              ? launch_pair<CI, CO, BK, dd::EPI_SPLIT>(ma_hi, ma_lo, L.mp_hi, L.mp_lo, a, e->sm_count, st)          \
+              : launch_pair<CI, CO, BK, dd::EPI_F32>(ma_hi, ma_lo, L.mp_hi, L.mp_lo, a, e->sm_count, st);           \
+    break;
+      switch (L.sid) {
+        PAIR_CASE(1, 64, 256, 32)
+        PAIR_CASE(2, 256, 256, 32)
+      }
+#undef PAIR_CASE
+    } else {
 #define HALO_CASE(ID, CI, CO, BK)                                                                                   \
   case ID:                                                                                                          \
     err = (epi == dd::EPI_F32_STATS)                                                                                \
@@ -588,6 +644,7 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
       HALO_CASE(4, 64, 16, 32)
     }
 #undef HALO_CASE
+    }
   } else {
     CUtensorMap ma_hi, ma_lo;
     int rc;
@@ -812,6 +869,10 @@ int pack_layer(dd_engine* e, ConvLayer& L, const float* w, const float* b, int c
   if ((rc = make_w_map(&L.mb_lo, L.w_lo, cout, cin, s.bk))) return rc;
   if ((rc = make_w_map(&L.mh_hi, L.w_hi, cout, cin, kHaloBK[L.sid]))) return rc;
   if ((rc = make_w_map(&L.mh_lo, L.w_lo, cout, cin, kHaloBK[L.sid]))) return rc;
+  if (cout == 256) {
+    if ((rc = make_w_map(&L.mp_hi, L.w_hi, cout, cin, kHaloBK[L.sid], cout / 2))) return rc;
+    if ((rc = make_w_map(&L.mp_lo, L.w_lo, cout, cin, kHaloBK[L.sid], cout / 2))) return rc;
+  }
   if (kSwapBK[L.sid] > 0) {
     if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_swap), static_cast<size_t>(9) * 128 * cin * 2))) return rc;
     dd::pack_swap_weight_kernel<<<128, 256, 0, st>>>(w, L.w_swap, cout, cin, scale);
@@ -1964,6 +2025,7 @@ int dd_conv3x3(dd_handle h, const float* x, const float* w, const float* b, floa
   a.split_scale = 1.f;
   a.status = status;
   a.fp8_probe = 0;
+  a.clk_probe = nullptr;
   cudaError_t err = cudaSuccess;
   const ShapeInfo s = kShapes[sid];
   if (h->cfg.flags & DD_FLAG_SIMT_CONV) {
@@ -2005,8 +2067,13 @@ int dd_conv3x3(dd_handle h, const float* x, const float* w, const float* b, floa
     a.num_tiles = a.tiles_x * a.tiles_y * batch;
     if ((rc = make_strip_map(&ma_hi, hi, batch, height, width, cin, hbk))) return rc;
     if ((rc = make_strip_map(&ma_lo, lo, batch, height, width, cin, hbk))) return rc;
-    if ((rc = make_w_map(&mb_hi, whi, cout, cin, hbk))) return rc;
-    if ((rc = make_w_map(&mb_lo, wlo, cout, cin, hbk))) return rc;
+    const bool pair = (h->cfg.flags & DD_FLAG_PAIR_WIDE) && cout == 256;
+    if ((rc = make_w_map(&mb_hi, whi, cout, cin, hbk, pair ? cout / 2 : 0))) return rc;
+    if ((rc = make_w_map(&mb_lo, wlo, cout, cin, hbk, pair ? cout / 2 : 0))) return rc;
+    if (pair) {
+      err = sid == 1 ? launch_pair<64, 256, 32, dd::EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, a, h->sm_count, st)
+                     : launch_pair<256, 256, 32, dd::EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, a, h->sm_count, st);
+    } else
     switch (sid) {
       case 0: err = launch_halo<16, 64, 16, dd::EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, a, h->sm_count, st); break;
       case 1: err = launch_halo<64, 256, 32, dd::EPI_F32>(ma_hi, ma_lo, mb_hi, mb_lo, a, h->sm_count, st); break;
@@ -2055,6 +2122,8 @@ int dd_bench_conv(dd_handle h, int32_t cin, int32_t cout, int32_t iters, float* 
     if ((rc = run_conv(h, layer, in_hi, in_lo, kActScale, split_out ? dd::EPI_SPLIT : dd::EPI_F32_STATS, h->Y,
                        h->stats[0], h->S_hi[0], h->S_lo[0], st)))
       return rc;
+  if (getenv("DD_CLK_PROBE") && !h->clk_probe) CUDA_TRY(cudaMalloc(&h->clk_probe, 16));
+  if (h->clk_probe) CUDA_TRY(cudaMemsetAsync(h->clk_probe, 0, 16, st));
   CUDA_TRY(cudaEventRecord(e0, st));
   for (int i = 0; i < iters; ++i)
     if ((rc = run_conv(h, layer, in_hi, in_lo, kActScale, split_out ? dd::EPI_SPLIT : dd::EPI_F32_STATS, h->Y,
@@ -2066,6 +2135,15 @@ int dd_bench_conv(dd_handle h, int32_t cin, int32_t cout, int32_t iters, float* 
   CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  if (h->clk_probe) {
+    unsigned long long v[2] = {0, 0};
+    CUDA_TRY(cudaMemcpy(v, h->clk_probe, 16, cudaMemcpyDeviceToHost));
+    if (v[1])
+      fprintf(stderr, "[clk_probe] conv %d->%d: %.0f SM cycles, %.1f us per launch (CTA 0) => %.0f MHz\n", cin, cout,
+              double(v[0]) / iters, double(v[1]) / iters * 1e-3, double(v[0]) / double(v[1]) * 1e3);
+    cudaFree(h->clk_probe);
+    h->clk_probe = nullptr;
+  }
   *ms_out = ms / iters;
   return DD_OK;
 }

@@ -67,7 +67,8 @@ enum dd_flags {
   DD_FLAG_SIMT_CONV = 1 << 1,  /* debug: fp32 CUDA-core convolutions instead of tcgen05 */
   DD_FLAG_CHECK_RANGE = 1 << 2,/* after the call, sync and report DD_ERR_RANGE if the split overflowed */
   DD_FLAG_HALO_CONV = 1 << 3,  /* loop convs on the row-halo-reuse kernel (16x8 tiles, 2.7x less activation traffic) */
-  DD_FLAG_SWAP_NARROW = 1 << 4 /* Cout <= 64 convs on the swapped-operand kernel (weights as A, 256 pixels as N) */
+  DD_FLAG_SWAP_NARROW = 1 << 4, /* Cout <= 64 convs on the swapped-operand kernel (weights as A, 256 pixels as N) */
+  DD_FLAG_PAIR_WIDE = 1 << 5    /* Cout = 256 convs on CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256) */
 };
 
 typedef struct dd_config {

@@ -34,13 +34,15 @@ def _head_sd(head):
 
 
 # ------------------------------------------------------------------------------------------------ single layers
-@pytest.mark.parametrize("path", ["classic", "halo", "swap", "simt"])
+@pytest.mark.parametrize("path", ["classic", "halo", "pair", "swap", "simt"])
 @pytest.mark.parametrize("cin,cout", SHAPES)
 def test_conv3x3_all_hot_path_shapes(cin, cout, path):
-    """3-pass fp16 split on tcgen05 — classic 8x16-tile kernel, row-halo-reuse kernel, swapped-operand kernel for the
-    narrow layers — and the fp32 CUDA-core check path, vs an fp64 reference; ragged tiles, a single tile, sub-tile images."""
+    """3-pass fp16 split on tcgen05 — classic 8x16-tile kernel, row-halo-reuse kernel, its CTA-pair (cta_group::2,
+    M = 256) variant for Cout = 256 (odd tile counts leave the second CTA of the last pair a zero-filled tile),
+    swapped-operand kernel for the narrow layers — and the fp32 CUDA-core check path, vs an fp64 reference; ragged
+    tiles, a single tile, sub-tile images."""
     eng = dd.DenoiseEngine("swin", 1, (8, 16), (4, 8), 2, DEV, cuda_graph=False, simt_conv=path == "simt",
-                           halo_conv=path == "halo", swap_narrow=path == "swap")
+                           halo_conv=path in ("halo", "pair"), swap_narrow=path == "swap", pair_wide=path == "pair")
     for (B, H, W) in [(2, 24, 40), (1, 8, 16), (1, 13, 21), (1, 5, 9), (2, 57, 76)]:
         g = torch.Generator().manual_seed(cin * 1000 + cout + H)
         x = torch.randn(B, cin, H, W, generator=g).to(DEV) * 3
