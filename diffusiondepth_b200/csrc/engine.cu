@@ -1814,8 +1814,8 @@ int dd_enable_backbone(dd_handle h, const dd_backbone_config* bc) {
     return DD_OK;
   }
   if (bc->kind != DD_BACKBONE_SWIN) return fail(DD_ERR_UNSUPPORTED, "unknown backbone kind");
-  if (!h->prod.enabled || !h->prod.neck || h->prod.nlev != 4)
-    return fail(DD_ERR_INVALID, "dd_enable_producers (4 levels, has_neck) must be called first");
+  if (!h->prod.enabled || h->prod.nlev != 4)
+    return fail(DD_ERR_INVALID, "dd_enable_producers (4 levels) must be called first");
   if (bc->embed_dims != 192 || bc->window != 7)
     return fail(DD_ERR_UNSUPPORTED, "native Swin is instantiated for embed_dims 192 (Swin-L), window 7");
   Backbone b;

@@ -71,6 +71,7 @@ class DDIMHeadBase(nn.Module):
 
     variant = "res"          # engine variant
     fpn_in_channels = (64, 128, 256, 512)
+    has_neck = False         # HAHI neck in front of the FPN (the *HAHI heads)
     return_intermediates = False  # *Vis heads: also decode every intermediate latent -> 'pred_inter'
 
     def __init__(self, in_channels=None, up_scale_factor=1, inference_steps=20, num_train_timesteps=1000,
@@ -195,7 +196,7 @@ class DDIMHeadBase(nn.Module):
             eng = DenoiseEngine(self.variant, batch, latent_hw, cond_hw, self.diffusion_inference_steps, device,
                                 cuda_graph=self.use_cuda_graph, check_range=False)
             if native:
-                eng.enable_producers(feats[0], feats[1], has_neck=self.variant == "swin")
+                eng.enable_producers(feats[0], feats[1], has_neck=self.has_neck)
             if image_hw is not None:
                 if self.variant == "swin":
                     eng.enable_backbone(image_hw)

@@ -9,6 +9,7 @@ from ._ddim_head import DDIMHeadBase
 @HEADS.register_module()
 class DDIMDepthEstimate_Swin_ADDHAHI(DDIMHeadBase):
     variant = "swin"
+    has_neck = True
     fpn_in_channels = (192, 384, 768, 1536)
 
     def __init__(self, **kwargs):

@@ -118,7 +118,7 @@ typedef struct dd_producer_config {
   int32_t channels[4];  /* backbone feature channels, finest level first */
   int32_t heights[4];
   int32_t widths[4];
-  int32_t has_neck;     /* 1: Swin/MPViT heads (HAHIHeteroNeck in front of the FPN), 0: Res heads */
+  int32_t has_neck;     /* 1: *HAHI heads (HAHIHeteroNeck in front of the FPN), 0: Res heads and Swin_ADD */
 } dd_producer_config;
 int dd_enable_producers(dd_handle h, const dd_producer_config* pc);
 
@@ -131,7 +131,7 @@ int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, 
 /* Optional: also run the Swin backbone natively (reference src/model/backbone/swin.py:756-777): patch embed,
  * LayerNorms, QKV / proj / FFN / patch-merging Linears on the 3-pass tensor-core GEMM path, 7x7 (shifted-)window
  * attention with relative-position bias and the finite -100 mask, per-stage output norms written straight into the
- * neck's input planes.  Requires dd_enable_producers(4 levels, has_neck = 1) with matching geometry; register the
+ * neck's (or, without a neck, the FPN's) input planes.  Requires dd_enable_producers(4 levels) with matching geometry; register the
  * reference keys of `depth_backbone.*` as "backbone.<key>" (the int64 `relative_position_index` buffers are not
  * needed).  Instantiated for Swin-L (embed_dims 192, head_dim 32, window 7). */
 enum dd_backbone_kind {

@@ -10,6 +10,10 @@ FAMILIES = {
     "res50": dict(backbone_module="mmbev_resnet", backbone_name="mmbev_res50", head_specify="DDIMDepthEstimate_Res"),
     "swinl": dict(backbone_module="swin", backbone_name="swin_large_naive_nopretrain",
                   head_specify="DDIMDepthEstimate_Swin_ADDHAHI"),
+    "swinl_add": dict(backbone_module="swin", backbone_name="swin_large_naive_nopretrain",
+                      head_specify="DDIMDepthEstimate_Swin_ADD"),
+    "mpvit_s": dict(backbone_module="mpvit", backbone_name="mpvit_small",
+                    head_specify="DDIMDepthEstimate_MPVIT_ADDHAHI"),
 }
 
 # name -> (family, T, batch, H, W).  C1..C5 = BASELINE.json configs[0..4]
@@ -29,6 +33,8 @@ GOLDEN = {
     "g_res50_c2": ("res50", 20, 1, 228, 304),       # image 0 of BASELINE config 2
     "g_swinl_c3": ("swinl", 20, 1, 352, 1216),      # image 0 of BASELINE config 3 / 4
     "g_swinl_c5": ("swinl", 50, 1, 480, 640),       # image 0 of BASELINE config 5 (50-step stress)
+    "g_swinl_add_small": ("swinl_add", 5, 1, 96, 160),   # Swin head without the HAHI neck
+    "g_mpvit_small": ("mpvit_s", 5, 1, 64, 112),    # MPViT-small + MPVIT_ADDHAHI head (cond at latent resolution)
 }
 
 

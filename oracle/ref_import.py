@@ -41,12 +41,30 @@ def make_args(backbone_module, backbone_name, head_specify, inference_steps=20,
 
 
 def build_reference_model(args):
-    """reference src/main.py:414 — `get_model(args)(args)`; returns the nn.Module in eval()."""
+    """reference src/main.py:414 — `get_model(args)(args)`; returns the nn.Module in eval().
+
+    The reference's MPViT factories `torch.load` an ImageNet checkpoint from a hard-coded path
+    (backbone/mpvit.py:756,788,826,859) that exists nowhere but on its authors' cluster; while such a model is being
+    constructed, loads of a missing `*mpvit_*.pth` return an empty {'model': {}} (load_state_dict(strict=False) of
+    nothing), i.e. the network keeps its constructor initialisation — the weights are overwritten by the caller's
+    load_state_dict(strict=True) anyway."""
     _activate()
     import importlib
+    import torch
     model_pkg = importlib.import_module("model")
     cls = model_pkg.get(args)
-    net = cls(args)
+    real_load = torch.load
+
+    def load(f, *a, **k):
+        if isinstance(f, str) and "mpvit_" in os.path.basename(f) and not os.path.isfile(f):
+            return {"model": {}}
+        return real_load(f, *a, **k)
+
+    torch.load = load
+    try:
+        net = cls(args)
+    finally:
+        torch.load = real_load
     net.eval()
     return net
 
@@ -63,4 +81,5 @@ def reference_modules():
     ns.swin = importlib.import_module("model.backbone.swin")
     ns.resnet = importlib.import_module("model.backbone.mmbev_resnet")
     ns.hahi = importlib.import_module("model.necks.hahi")
+    ns.mpvit = importlib.import_module("model.backbone.mpvit")
     return ns

@@ -299,7 +299,7 @@ def _run_plugin(case, batch=None):
 
 
 @pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_swinl_small", "g_res50_c2", "g_swinl_c3",
-                                  "g_swinl_c5"])
+                                  "g_swinl_c5", "g_swinl_add_small", "g_mpvit_small"])
 def test_plugin_forward_matches_reference_golden(case):
     """`Diffusion_DCbase_Model.forward(sample)` on the GPU vs the real reference's own forward (golden)."""
     g, m, out = _run_plugin(case)

@@ -10,7 +10,7 @@ import dd_helpers as helpers
 TOL_Z = 5e-5  # fp32-vs-fp32 re-association noise on the logits (3e-5 vs fp64 over 20 steps)
 
 
-@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged"])
+@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small"])
 def test_oracle_reproduces_reference_golden(case):
     g = helpers.load_golden(case)
     m = helpers.build_mirror(g["family"], g["T"])
@@ -35,7 +35,7 @@ def test_oracle_reproduces_reference_golden(case):
         'pred_init', 'pred_inter', 'pred_uncertainty', 'weight_map'])
 
 
-@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged"])
+@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small"])
 def test_mirror_producers_match_reference_condition(case):
     """backbone + FPN of the product mirror (torch ops, once per image) reproduce the reference's cond map."""
     g = helpers.load_golden(case)

@@ -16,8 +16,9 @@ OUTPUT_KEYS = ['aff', 'blur_depth_t', 'confidence', 'ddim_loss', 'gamma', 'gt_ma
 
 
 def test_registries_expose_reference_names():
+    # every head reference src/model/head/__init__.py registers
     for name in ("DDIMDepthEstimate_Res", "DDIMDepthEstimate_Swin_ADDHAHI", "DDIMDepthEstimate_ResVis",
-                 "DDIMDepthEstimate_Swin_ADDHAHIVis"):
+                 "DDIMDepthEstimate_Swin_ADDHAHIVis", "DDIMDepthEstimate_Swin_ADD", "DDIMDepthEstimate_MPVIT_ADDHAHI"):
         assert name in HEADS
     assert "DeepDepthTransformWithUpsampling" in DEPTH_TRANSFORM
     codec = DEPTH_TRANSFORM.build(dict(type='DeepDepthTransformWithUpsampling', hidden=16, eps=1e-6))
@@ -64,7 +65,7 @@ def test_heads_have_no_cpu_fallback():
 
 
 @pytest.mark.skipif(not ref_import.available(), reason="reference sources not present")
-@pytest.mark.parametrize("family", ["res18", "swinl"])
+@pytest.mark.parametrize("family", ["res18", "swinl", "swinl_add", "mpvit_s"])
 def test_state_dict_matches_reference_key_for_key(family):
     f = configs.FAMILIES[family]
     ref = ref_import.build_reference_model(ref_import.make_args(f["backbone_module"], f["backbone_name"],
