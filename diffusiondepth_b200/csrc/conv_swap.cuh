@@ -9,10 +9,13 @@
 // K-step give all four partial products (hi*hi, lo*hi in accumulator rows 0..63... and hi*lo, lo*lo in rows 64..127):
 // 2 x ~165 cycles per 256 pixels = 165 per 128 pixels, and the result is exact to the full 22-bit operands.
 //
-// TMEM accumulator: lane = output channel (rows 0..63 from W_hi, 64..127 from W_lo), column = pixel.  The epilogue
-// adds the two halves through shared memory; since lane == channel, each store instruction writes 32 consecutive
-// channels of one pixel: NHWC-coalesced with no transpose.  GroupNorm partial sums: per-thread over its pixels, then
-// a shuffle reduction over the lanes of a group.
+// TMEM accumulator: lane = weight row, column = pixel.  The rows are ordered so that every 32-lane quarter (= what one
+// epilogue warp can read) is self-contained: lanes 0..15 of quarter q hold W_hi of 16 output channels, lanes 16..31 the
+// W_lo rows of the SAME channels, so hi + lo is one warp shuffle (no shared-memory exchange between warps, no block
+// barrier per chunk — that exchange made the two tiny layers epilogue-bound).  Cout = 64: quarter q owns channels
+// 16q..16q+15 (= GroupNorm group q) for all 256 pixels.  Cout = 16: the 32 rows are replicated in all four quarters
+// (M = 128 costs the same as M = 32) and quarter q finishes pixels 64q..64q+63.  Stores go through a warp-private
+// [32 px][16 ch] transpose so each lane writes a float4.
 #pragma once
 #include "conv_umma.cuh"
 
@@ -32,7 +35,7 @@ struct SwapCfg {
   static constexpr int W_BYTES = 128 * ROW_BYTES;        // [W_hi ; W_lo] tile (A operand)
   static constexpr int P_BYTES = SWAP_N * ROW_BYTES;     // one pixel plane tile (B operand)
   static constexpr int STAGE_BYTES = W_BYTES + 2 * P_BYTES;
-  static constexpr int XCH_BYTES = 4 * 32 * 33 * 4 + 2 * 32 * 2 * 4;  // 2 pairs x 2 parities x [32 lanes][32 px (+pad)] + stats scratch
+  static constexpr int XCH_BYTES = 4 * 32 * 16 * 4 + 4 * 4 * 2 * 4;  // 4 warps x [32 px][16 ch] transpose + stats scratch [4 warps][4 groups][2]
   static constexpr int STAGES_RAW = (220 * 1024 - XCH_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static_assert(STAGES >= 2, "stage too large");
@@ -140,19 +143,17 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
       buf ^= 1;
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: lane = output channel, column = pixel.
-    // TMEM lane quarters q = 0,1 hold the W_hi rows (channels 32q + lane), q = 2,3 the W_lo rows of the same channels.
-    // Per 32-pixel chunk (= 2 tile rows of 16) the two halves swap 16 pixels each through shared memory, so that all
-    // four warps add and store: q < 2 finish pixels 0..15 of the chunk, q >= 2 pixels 16..31.  Double-buffered exchange
-    // tile -> one named barrier per chunk.
+    // ------------------------------------------------------------------ epilogue (see the header: quarter-local hi/lo rows)
     const int q = warp & 3;
-    const int ch = (q & 1) * 32 + lane;
-    const bool has_ch = ch < COUT;
-    const bool upper = q >= 2;           // which half of the chunk's pixels this warp finishes
-    float* Xbase = xch + (q & 1) * (2 * 32 * 33);  // [parity][lane][32 (+1 pad)]
+    const int cl = lane & 15;                         // channel within this quarter's 16
+    const int cb = COUT == 64 ? 16 * q : 0;           // first channel of this warp
+    constexpr int CHUNKS = COUT == 64 ? 8 : 2;        // 32-pixel chunks this warp finishes per tile
+    const int col0 = COUT == 64 ? 0 : 64 * q;         // first pixel column of this warp
+    float* X = xch + q * (32 * 16);
+    float* R = xch + 4 * 32 * 16;                     // [4 warps][4 groups][2]
     uint32_t full_phase = 0;
-    int buf = 0, par = 0;
-    const float bias = has_ch ? __ldg(p.bias + ch) : 0.f;
+    int buf = 0;
+    const float bias = __ldg(p.bias + cb + cl);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
       const int x0 = tx * SWAP_TW, y0 = ty * SWAP_TH;
@@ -162,51 +163,71 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
       float s1 = 0.f, s2 = 0.f;
       const uint32_t xmask = (x0 + 16 <= p.W) ? 0xFFFFu : ((1u << (p.W - x0)) - 1u);  // valid columns of this tile
 #pragma unroll 1
-      for (int c0 = 0; c0 < SWAP_N; c0 += 32) {
+      for (int cc = 0; cc < CHUNKS; ++cc) {
+        const int c0 = col0 + cc * 32;                // chunk = two tile rows of 16 pixels
         uint32_t rr[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * SWAP_N + c0), rr);
         tmem_ld_wait();
-        float* X = Xbase + par * (32 * 33);
-        // hand the partner the 16 pixels it will finish: hi-warps give pixels 16..31, lo-warps give pixels 0..15
+        const int yr = y0 + (c0 >> 4);
+        const bool row_ok0 = yr < p.H, row_ok1 = yr + 1 < p.H;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) X[lane * 33 + (upper ? j : 16 + j)] = __uint_as_float(rr[upper ? j : 16 + j]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int y = y0 + (c0 >> 4) + (upper ? 1 : 0);  // chunk = two tile rows; this warp owns one of them
-        if (y < p.H && has_ch) {
-          float* dst = p.y32 + ((static_cast<size_t>(img) * p.H + y) * p.W + x0) * COUT + ch;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int jj = upper ? 16 + j : j;
-            const float v = fmaf(__uint_as_float(rr[jj]) + X[lane * 33 + jj], p.acc_scale, bias);
-            if ((xmask >> j) & 1u) {
-              dst[j * COUT] = v;
+        for (int j = 0; j < 32; ++j) {
+          const float a = __uint_as_float(rr[j]);
+          const float v = fmaf(a + __shfl_down_sync(0xffffffffu, a, 16), p.acc_scale, bias);  // lanes 0..15: hi + lo
+          if (lane < 16) {
+            X[j * 16 + cl] = v;
+            if ((j < 16 ? row_ok0 : row_ok1) && ((xmask >> (j & 15)) & 1u)) {
               s1 += v;
               s2 = fmaf(v, v, s2);
             }
           }
         }
-        par ^= 1;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int px = (lane >> 2) + 8 * i;         // 0..31: tile row (px >> 4), column (px & 15)
+          const int y = yr + (px >> 4), x = px & 15;
+          if (y < p.H && ((xmask >> x) & 1u)) {
+            const float4 v4 = *reinterpret_cast<const float4*>(X + px * 16 + (lane & 3) * 4);
+            *reinterpret_cast<float4*>(p.y32 + ((static_cast<size_t>(img) * p.H + y) * p.W + x0 + x) * COUT + cb +
+                                       (lane & 3) * 4) = v4;
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
       if constexpr (EPI == EPI_F32_STATS) {
-        // GroupNorm(4, COUT): GROUP_CH consecutive channels = consecutive lanes; then add the two pixel halves
+        if constexpr (COUT == 64) {  // this warp's 16 channels are exactly GroupNorm group q, over the whole tile
 #pragma unroll
-        for (int o = C::GROUP_CH / 2; o > 0; o >>= 1) {
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        float* R = xch + 4 * 32 * 33;  // [2 (q&1)][32 lanes][2] scratch for the lo-warps' sums
-        if (upper) {
-          R[((q & 1) * 32 + lane) * 2 + 0] = s1;
-          R[((q & 1) * 32 + lane) * 2 + 1] = s2;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (!upper && has_ch && (lane % C::GROUP_CH) == 0) {
-          const int g = ch / C::GROUP_CH;
-          p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + 0] = s1 + R[((q & 1) * 32 + lane) * 2 + 0];
-          p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + 1] = s2 + R[((q & 1) * 32 + lane) * 2 + 1];
+          for (int o = 8; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (lane == 0) {
+            p.stats_partial[(static_cast<size_t>(tile) * 4 + q) * 2 + 0] = s1;
+            p.stats_partial[(static_cast<size_t>(tile) * 4 + q) * 2 + 1] = s2;
+          }
+        } else {                     // groups of 4 channels; each warp saw a quarter of the tile's pixels
+#pragma unroll
+          for (int o = 2; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (lane < 16 && (lane & 3) == 0) {
+            R[(q * 4 + (lane >> 2)) * 2 + 0] = s1;
+            R[(q * 4 + (lane >> 2)) * 2 + 1] = s2;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (q == 0 && lane < 8) {
+            const int g = lane >> 1, which = lane & 1;
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) t += R[(w * 4 + g) * 2 + which];
+            p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + which] = t;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // R is reused by the next tile
         }
       }
       buf ^= 1;
@@ -221,20 +242,19 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
   }
 }
 
-// w [COUT][CIN][3][3] fp32 -> fp16 [tap][128][CIN]: row co = hi(s*w), row 64+co = lo; other rows zero
+// w [COUT][CIN][3][3] fp32 -> fp16 [tap][128][CIN].  Row r = 32q + i: part = i / 16 (0: hi, 1: lo), channel =
+// (cout == 64 ? 16q : 0) + i % 16 — every 32-row quarter carries hi and lo of the same 16 channels (cout == 16: the same
+// 32 rows in all four quarters).
 __global__ void pack_swap_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int cout, int cin,
                                         float scale) {
   const int n = 9 * 128 * cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int ci = i % cin, row = (i / cin) % 128, tap = i / (cin * 128);
-    const int co = row & 63;
-    float r = 0.f;
-    if (co < cout) {
-      const float s = w[(static_cast<size_t>(co) * cin + ci) * 9 + tap] * scale;
-      const __half h = __float2half_rn(s);
-      r = row < 64 ? __half2float(h) : s - __half2float(h);
-    }
-    out[i] = __float2half_rn(r);
+    const int q = row >> 5, part = (row >> 4) & 1;
+    const int co = (cout == 64 ? 16 * q : 0) + (row & 15);
+    const float s = w[(static_cast<size_t>(co) * cin + ci) * 9 + tap] * scale;
+    const __half h = __float2half_rn(s);
+    out[i] = part == 0 ? h : __float2half_rn(s - __half2float(h));
   }
 }
 

@@ -182,10 +182,11 @@ cudaError_t launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
 }
 constexpr int kHaloBK[5] = {16, 32, 32, 32, 32};  // K chunk of the halo kernel per shape id
 constexpr int kSwapBK[5] = {16, 0, 0, 32, 32};    // K chunk of the swapped-operand kernel (narrow-N shapes only)
-// Which kernel serves which shape inside the engine when the flags allow it (measured, profiles/README.md): the
-// swapped-operand kernel wins only where the mainloop dominates (256->64); the two tiny layers are epilogue-bound
-// and stay on the classic kernel; row-halo reuse pays for the wide layers.
-constexpr bool kUseSwap[5] = {false, false, false, true, false};
+// Which kernel serves which shape inside the engine when the flags allow it (measured, profiles/README.md,
+// tiny_probe.py): the swapped-operand kernel wins where MMA issue dominates (256->64: 356 vs 700 us; 64->16: 92 vs 129 us
+// with the quarter-local epilogue); 16->64 stays on the classic kernel (90 us; swap 182, halo 88); row-halo reuse pays
+// for the wide layers.
+constexpr bool kUseSwap[5] = {false, false, false, true, true};
 constexpr bool kUseHalo[5] = {false, true, true, false, false};
 // CTA pairs (cta_group::2) measured in cycles (profiles/clk_probe.py): 64->256 -6 % (its short K leaves the epilogue
 // exposed and halving the weight traffic through shared memory helps it), 256->256 +7 % (already at ~81 % tensor-pipe
@@ -556,9 +557,13 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
   for (int i = 0; i < 4; ++i)
     if (stats_partial == e->stats[i]) which = i;
   if (which >= 0) e->stats_tiles_img[which] = g.tiles_img;
+  bool swap_here = kUseSwap[L.sid];
+  if (const char* m = getenv("DD_SWAP_MASK")) swap_here = (atoi(m) >> L.sid) & 1;  // tuning probe (profiles/swap_probe.py)
   const bool use_swap = (e->cfg.flags & DD_FLAG_SWAP_NARROW) && !(e->cfg.flags & DD_FLAG_SIMT_CONV) &&
-                        kUseSwap[L.sid] && epi != dd::EPI_SPLIT;
-  const bool use_halo = (e->cfg.flags & DD_FLAG_HALO_CONV) && !(e->cfg.flags & DD_FLAG_SIMT_CONV) && kUseHalo[L.sid];
+                        swap_here && kSwapBK[L.sid] > 0 && epi != dd::EPI_SPLIT;
+  bool halo_here = kUseHalo[L.sid];
+  if (const char* m = getenv("DD_HALO_MASK")) halo_here = (atoi(m) >> L.sid) & 1;  // tuning probe
+  const bool use_halo = (e->cfg.flags & DD_FLAG_HALO_CONV) && !(e->cfg.flags & DD_FLAG_SIMT_CONV) && halo_here;
   if (!use_swap) {  // tile geometry of the kernel actually launched
     const int tw = use_halo ? dd::HALO_TW : dd::TILE_W, th = use_halo ? dd::HALO_TH : dd::TILE_H;
     a.tiles_x = (g.w + tw - 1) / tw;
