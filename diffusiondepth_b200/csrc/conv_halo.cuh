@@ -27,8 +27,11 @@ constexpr int HALO_TW = 8;
 // = ~860 cycles at 128 B/clk, above the 768 cycles of tensor work -> it is shared-memory-port bound.
 template <int CIN, int COUT, int BK, bool PAIR = false>
 struct HaloCfg {
-  static_assert(CIN % BK == 0 && (BK == 16 || BK == 32), "bad K chunk");
-  static constexpr int KC = CIN / BK;
+  static_assert((CIN % BK == 0 || CIN < BK) && CIN % 16 == 0 && (BK == 16 || BK == 32), "bad K chunk");
+  // CIN < BK (16-channel latent, BK = 32) is supported — the box is wider than the channel extent, TMA zero-fills the
+  // rest and only CIN / 16 K-steps are issued — but measured slower on 16->64 (110 vs 82 us), so the engine keeps BK = 16.
+  static constexpr int KC = (CIN + BK - 1) / BK;
+  static constexpr int KSTEPS = (CIN < BK ? CIN : BK) / 16;
   static constexpr int ROW_BYTES = BK * 2;
   static constexpr int STRIP_ROWS = (HALO_TH + 2) * HALO_TW;        // 144 pixel rows
   static constexpr int STRIP_BYTES = STRIP_ROWS * ROW_BYTES;        // one plane, one dx
@@ -39,10 +42,17 @@ struct HaloCfg {
   static constexpr int B_TILE_PAD = (B_TILE + 1023) / 1024 * 1024;
   static constexpr int B_SLOT = 2 * B_TILE_PAD;
   static constexpr int A_SLOTS = PAIR ? 3 : 2;
-  static constexpr int XPOSE_BYTES = 4 * 32 * 32 * 4;
+  static constexpr int EPI_SETS = (COUT == 64) ? 2 : 1;  // as ConvCfg: Cout = 64 drains its two 32-channel chunks in parallel
+  static constexpr int EPI_WARPS = 4 * EPI_SETS;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;
   static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - XPOSE_BYTES - A_SLOTS * A_SLOT;
   static constexpr int B_SLOTS_RAW = BUDGET / B_SLOT;
-  static constexpr int B_SLOTS = B_SLOTS_RAW > 8 ? 8 : B_SLOTS_RAW;
+  // Small layers (16->64, 64->16): all 9 x KC weight tiles fit in shared memory -> fetch them ONCE per CTA instead of once
+  // per tile.  Each cp.async.bulk.tensor costs its issuing thread ~160 ns, and 18 weight copies per 128-pixel tile were
+  // the whole tile time of the 16->64 layer (tensor pipe 12.5 % active).
+  static constexpr bool B_RESIDENT = !PAIR && (9 * KC * B_SLOT <= 40 * 1024) && (9 * KC <= B_SLOTS_RAW);
+  static constexpr int B_SLOTS = B_RESIDENT ? 9 * KC : (B_SLOTS_RAW > 8 ? 8 : B_SLOTS_RAW);
   static_assert(B_SLOTS >= 2, "B ring too small");
   static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 512 + XPOSE_BYTES;
   static constexpr int A_TX = 6 * STRIP_BYTES;
@@ -59,7 +69,7 @@ struct HaloCfg {
 };
 
 template <int CIN, int COUT, int BK, int EPI, bool PAIR = false>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__((HaloCfg<CIN, COUT, BK, PAIR>::THREADS), 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const ConvArgs p) {
@@ -104,7 +114,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], PAIR ? 8 : 4);
+      mbar_init(&tempty_bar[b], PAIR ? 8 : C::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -159,6 +169,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     int sb = 0;
     uint32_t pb = 0;
     DD_TILE_LOOP {
+      if (C::B_RESIDENT && tile != static_cast<int>(blockIdx.x)) break;  // weights stay in their slots after the first tile
       for (int kc = 0; kc < C::KC; ++kc) {
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_empty[sb], pb ^ 1);
@@ -194,14 +205,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const uint32_t a_base = smem_u32(a_ring + sa * C::A_SLOT);
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3, dx = tap % 3;
-          mbar_wait(&b_full[sb], pb);
+          mbar_wait(&b_full[sb], C::B_RESIDENT ? 0u : pb);  // resident: phase 0 completes once and stays complete
           tc_fence_after();
           // strip dx, dy rows down: 8-pixel groups stay dense (8 * ROW_BYTES) and aligned to the swizzle repeat
           const uint32_t sa_hi = a_base + (2 * dx) * C::STRIP_PAD + dy * HALO_TW * C::ROW_BYTES;
           const uint32_t sa_lo = sa_hi + C::STRIP_PAD;
           const uint32_t sb_hi = smem_u32(b_ring + sb * C::B_SLOT);
           const uint32_t sb_lo = sb_hi + C::B_TILE_PAD;
-          if (!PAIR && p.fp8_probe) {
+          if (!PAIR && p.fp8_probe == 1) {
             // DESIGN probe (DD_FP8_PROBE=1): fp16 hi*hi (2 x K16) + the two correction products as ONE e4m3 MMA each
             // (K = 32): 4 instructions per chunk instead of 6.  Operand bytes are reinterpreted, results are garbage.
             constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) | (static_cast<uint32_t>(TILE_M >> 4) << 24);
@@ -213,7 +224,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             umma_f8(d_tmem, umma_smem_desc(sa_hi, C::ROW_BYTES), umma_smem_desc(sb_lo, C::ROW_BYTES), idesc8, 1u);
           } else
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
+          for (int k = 0; k < C::KSTEPS; ++k) {
             const uint64_t a_hi = umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES);
             const uint64_t a_lo = umma_smem_desc(sa_lo + k * 32, C::ROW_BYTES);
             const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
@@ -233,7 +244,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
             }
           }
-          if constexpr (PAIR) umma_commit_pair(&b_empty[sb], 3); else umma_commit(&b_empty[sb]);
+          if constexpr (PAIR) umma_commit_pair(&b_empty[sb], 3);
+          else if constexpr (!C::B_RESIDENT) umma_commit(&b_empty[sb]);
           if (++sb == C::B_SLOTS) {
             sb = 0;
             pb ^= 1;
@@ -257,11 +269,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (as conv_umma.cuh, 16x8 tile)
     const int q = warp & 3;
+    const int es = (warp - 4) >> 2;  // epilogue set (see ConvCfg::EPI_SETS)
+    constexpr int NCH = COUT / C::CH;
+    static_assert(C::EPI_SETS == 1 || NCH == C::EPI_SETS, "one chunk per set");
     const int m = q * 32 + lane;
     const int r = m >> 3, c = m & 7;
     uint32_t full_phase = 0;
     int buf = 0, par = 0;
-    float* T = xpose + q * 1024;
+    float* T = xpose + (es * 4 + q) * 1024;
     long long clk0 = 0;
     unsigned long long ns0 = 0;
     const bool probe = p.clk_probe != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
@@ -284,8 +299,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       float tsum[4] = {0.f, 0.f, 0.f, 0.f}, tsq[4] = {0.f, 0.f, 0.f, 0.f};
       bool overflow = false;
 #pragma unroll
-      for (int ci = 0; ci < COUT / C::CH; ++ci) {
-        const int ch0 = ci * C::CH;
+      for (int cj = 0; cj < NCH / C::EPI_SETS; ++cj) {
+        const int ch0 = (cj * C::EPI_SETS + es) * C::CH;
         float v[C::CH];
 #pragma unroll
         for (int j = 0; j < C::CH; ++j) v[j] = 0.f;
@@ -313,7 +328,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           if (valid) {
 #pragma unroll
             for (int j = 0; j < C::CH; ++j) {
-              const int g = (ch0 + j) / C::GROUP_CH;
+              const int g = C::EPI_SETS == 1 ? (cj * C::CH + j) / C::GROUP_CH : j / C::GROUP_CH;
               tsum[g] += v[j];
               tsq[g] = fmaf(v[j], v[j], tsq[g]);
             }
@@ -372,17 +387,25 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           }
           if (lane == 0) {
-            red[((par * 4 + q) * 4 + g) * 2 + 0] = s;
-            red[((par * 4 + q) * 4 + g) * 2 + 1] = s2;
+            if constexpr (C::EPI_SETS == 1) {
+              red[((par * 4 + q) * 4 + g) * 2 + 0] = s;
+              red[((par * 4 + q) * 4 + g) * 2 + 1] = s2;
+            } else if (g < 2) {
+              red[((par * 8 + es * 4 + q) * 2 + g) * 2 + 0] = s;
+              red[((par * 8 + es * 4 + q) * 2 + g) * 2 + 1] = s2;
+            }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if constexpr (C::EPI_SETS == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 1, 256;" ::: "memory");
         const int e = threadIdx.x - 128;
         if (e < 8 && tile < p.num_tiles) {
           const int g = e >> 1, which = e & 1;
           float t = 0.f;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) t += red[((par * 4 + w) * 4 + g) * 2 + which];
+          for (int w = 0; w < 4; ++w)
+            t += C::EPI_SETS == 1 ? red[((par * 4 + w) * 4 + g) * 2 + which]
+                                  : red[((par * 8 + (g >> 1) * 4 + w) * 2 + (g & 1)) * 2 + which];
           p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + which] = t;
         }
         par ^= 1;

@@ -50,9 +50,13 @@ struct ConvArgs {
 
 template <int CIN, int COUT, int BK>
 struct ConvCfg {
-  static_assert(CIN % BK == 0 && (BK == 16 || BK == 32 || BK == 64), "bad K chunk");
+  static_assert((CIN % BK == 0 || CIN < BK) && CIN % 16 == 0 && (BK == 16 || BK == 32 || BK == 64), "bad K chunk");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "bad N");
-  static constexpr int KC = CIN / BK;                 // channel chunks per tap
+  // CIN < BK (the 16-channel latent with BK = 32): the TMA box is wider than the tensor's channel extent, the missing
+  // channels arrive as out-of-bounds zeros and only the first CIN / 16 K-steps are issued.  (Tried for the 16->64 layer:
+  // slower, 125 vs 88 us — that mainloop is bound by the bytes TMA pulls from L2, and this doubles them.)
+  static constexpr int KC = (CIN + BK - 1) / BK;      // channel chunks per tap
+  static constexpr int KSTEPS = (CIN < BK ? CIN : BK) / 16;  // MMA K-steps per chunk
   static constexpr int K_ITERS = 9 * KC;              // pipeline stages consumed per tile
   static constexpr int ROW_BYTES = BK * 2;            // one operand row = swizzle span
   static constexpr int A_BYTES = TILE_M * ROW_BYTES;  // one plane
@@ -62,7 +66,13 @@ struct ConvCfg {
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static_assert(STAGES >= 2, "stage too large");
-  static constexpr int XPOSE_BYTES = 4 * 32 * 32 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (coalesced y stores)
+  // Epilogue warps.  ncu (profiles/README.md): for Cout = 64 the mainloop is 27 short MMAs per tile and the epilogue ran at
+  // one warp per scheduler, i.e. at single-warp instruction latency (tensor pipe 12.5 % active) -> two sets of four warps,
+  // each set drains one 32-channel chunk of the tile.
+  static constexpr int EPI_SETS = (COUT == 64) ? 2 : 1;
+  static constexpr int EPI_WARPS = 4 * EPI_SETS;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;  // per-epilogue-warp 32x32 fp32 transpose tile (coalesced y stores)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers + scratch*/ + XPOSE_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   // Narrow-N layers: back-to-back MMAs into ONE accumulator serialise on its read-modify-write latency (~105 cycles
@@ -77,7 +87,7 @@ struct ConvCfg {
 };
 
 template <int CIN, int COUT, int BK, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__((ConvCfg<CIN, COUT, BK>::THREADS), 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const ConvArgs p) {
@@ -106,7 +116,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);
+      mbar_init(&tempty_bar[b], C::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -173,7 +183,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
         const uint32_t sb_lo = sb_hi + C::B_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
+        for (int k = 0; k < C::KSTEPS; ++k) {
           const uint64_t a_hi = umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES);
           const uint64_t a_lo = umma_smem_desc(sa_lo + k * 32, C::ROW_BYTES);
           const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
@@ -200,8 +210,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       buf ^= 1;
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes per set)
     const int q = warp & 3;
+    const int es = (warp - 4) >> 2;  // epilogue set: which channel chunks of the tile this warp drains
+    constexpr int NCH = COUT / C::CH;
+    static_assert(C::EPI_SETS == 1 || NCH == C::EPI_SETS, "one chunk per set");
     const int m = q * 32 + lane;
     const int r = m >> 4, c = m & 15;
     uint32_t full_phase = 0;
@@ -216,7 +229,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const size_t pix = (static_cast<size_t>(img) * p.H + y) * p.W + x;
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       const uint32_t row_off = static_cast<uint32_t>(pix * COUT);  // < 2^32 elements for every tensor of the path
-      float* T = xpose + q * 1024;
+      float* T = xpose + (es * 4 + q) * 1024;
 
       mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
       full_phase ^= (1u << buf);
@@ -224,9 +237,16 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
       float tsum[4] = {0.f, 0.f, 0.f, 0.f}, tsq[4] = {0.f, 0.f, 0.f, 0.f};
       bool overflow = false;
+      if (p.fp8_probe == 2) {  // timing probe (DD_FP8_PROBE=2): no epilogue work at all -> the mainloop's own tile rate
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        buf ^= 1;
+        continue;
+      }
 #pragma unroll
-      for (int ci = 0; ci < COUT / C::CH; ++ci) {
-        const int ch0 = ci * C::CH;
+      for (int cj = 0; cj < NCH / C::EPI_SETS; ++cj) {
+        const int ch0 = (cj * C::EPI_SETS + es) * C::CH;  // compile-time when there is one set (es == 0)
         float v[C::CH];
 #pragma unroll
         for (int j = 0; j < C::CH; ++j) v[j] = 0.f;
@@ -255,7 +275,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           if (valid) {
 #pragma unroll
             for (int j = 0; j < C::CH; ++j) {
-              const int g = (ch0 + j) / C::GROUP_CH;  // compile-time: both loops are fully unrolled
+              // compile-time (both loops are fully unrolled); with two sets: the chunk-local group 0 / 1
+              const int g = C::EPI_SETS == 1 ? (cj * C::CH + j) / C::GROUP_CH : j / C::GROUP_CH;
               tsum[g] += v[j];
               tsq[g] = fmaf(v[j], v[j], tsq[g]);
             }
@@ -317,17 +338,25 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           }
           if (lane == 0) {
-            red[((par * 4 + q) * 4 + g) * 2 + 0] = s;
-            red[((par * 4 + q) * 4 + g) * 2 + 1] = s2;
+            if constexpr (C::EPI_SETS == 1) {
+              red[((par * 4 + q) * 4 + g) * 2 + 0] = s;
+              red[((par * 4 + q) * 4 + g) * 2 + 1] = s2;
+            } else if (g < 2) {  // set es holds GroupNorm groups 2 es, 2 es + 1 as its local groups 0, 1
+              red[((par * 8 + es * 4 + q) * 2 + g) * 2 + 0] = s;
+              red[((par * 8 + es * 4 + q) * 2 + g) * 2 + 1] = s2;
+            }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-        const int e = threadIdx.x - 128;                // 0..127
+        if constexpr (C::EPI_SETS == 1) asm volatile("bar.sync 1, 128;" ::: "memory");  // the epilogue warps only
+        else asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int e = threadIdx.x - 128;                // 0..127 (.. 255)
         if (e < 8) {
           const int g = e >> 1, which = e & 1;
           float t = 0.f;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) t += red[((par * 4 + w) * 4 + g) * 2 + which];
+          for (int w = 0; w < 4; ++w)
+            t += C::EPI_SETS == 1 ? red[((par * 4 + w) * 4 + g) * 2 + which]
+                                  : red[((par * 8 + (g >> 1) * 4 + w) * 2 + (g & 1)) * 2 + which];
           p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + which] = t;
         }
         par ^= 1;  // double-buffered scratch: one barrier per tile is enough

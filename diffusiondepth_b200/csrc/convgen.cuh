@@ -79,7 +79,7 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
     tma_prefetch_desc(&tmB_hi);
     tma_prefetch_desc(&tmB_lo);
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);  // two producer threads (activation planes / weight planes) arrive per stage
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -98,7 +98,10 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
 
-  if (warp == 0 && lane == 0) {
+  if ((warp == 0 || warp == 3) && lane == 0) {
+    // two TMA producers: warp 0 issues the activation copies, warp 3 the weight copies.  Each cp.async.bulk.tensor costs
+    // its issuing thread ~160 ns; four per 32-channel stage from one thread (0.64 us) were slower than the stage's MMAs
+    const bool act = (warp == 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
@@ -110,17 +113,20 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
         for (int kc = 0; kc < kc_total; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = stage_ptr(stage);
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           const int ax = x0 * p.stride + dx, ay = y0 * p.stride + dy;
-          if (kc < p.kc0) {
+          if (!act) {
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_BYTES);
+            tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * C::BK, nt * NT, tap);
+            tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * C::BK, nt * NT, tap);
+          } else if (kc < p.kc0) {
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
             tma_load_4d(s, &tmA0_hi, &full_bar[stage], kc * C::BK, ax, ay, img);
             tma_load_4d(s + C::A_BYTES, &tmA0_lo, &full_bar[stage], kc * C::BK, ax, ay, img);
           } else {
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
             tma_load_4d(s, &tmA1_hi, &full_bar[stage], (kc - p.kc0) * C::BK, ax, ay, img);
             tma_load_4d(s + C::A_BYTES, &tmA1_lo, &full_bar[stage], (kc - p.kc0) * C::BK, ax, ay, img);
           }
-          tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * C::BK, nt * NT, tap);
-          tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * C::BK, nt * NT, tap);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;

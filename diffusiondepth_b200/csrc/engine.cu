@@ -177,17 +177,18 @@ cudaError_t launch_umma(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
   using C = dd::ConvCfg<CIN, COUT, BK>;
   auto kern = dd::conv3x3_umma_kernel<CIN, COUT, BK, EPI>;  // smem attribute set in configure_all_kernels()
   int grid = args.num_tiles < sm_count ? args.num_tiles : sm_count;
-  kern<<<grid, 256, C::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, args);
+  kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, args);
   return cudaGetLastError();
 }
 constexpr int kHaloBK[5] = {16, 32, 32, 32, 32};  // K chunk of the halo kernel per shape id
 constexpr int kSwapBK[5] = {16, 0, 0, 32, 32};    // K chunk of the swapped-operand kernel (narrow-N shapes only)
 // Which kernel serves which shape inside the engine when the flags allow it (measured, profiles/README.md,
 // tiny_probe.py): the swapped-operand kernel wins where MMA issue dominates (256->64: 356 vs 700 us; 64->16: 92 vs 129 us
-// with the quarter-local epilogue); 16->64 stays on the classic kernel (90 us; swap 182, halo 88); row-halo reuse pays
-// for the wide layers.
+// with the quarter-local epilogue); 16->64: halo kernel with the weights resident in shared memory and two epilogue warp
+// sets, 82 us (classic 88, swap 182; its MMAs cost ~210 cycles each on 32-byte operand rows — padding K to 64-byte rows
+// through TMA zero fill was slower still, 110-125 us); row-halo reuse pays for the wide layers.
 constexpr bool kUseSwap[5] = {false, false, false, true, true};
-constexpr bool kUseHalo[5] = {false, true, true, false, false};
+constexpr bool kUseHalo[5] = {true, true, true, false, false};
 // CTA pairs (cta_group::2) measured in cycles (profiles/clk_probe.py): 64->256 -6 % (its short K leaves the epilogue
 // exposed and halving the weight traffic through shared memory helps it), 256->256 +7 % (already at ~81 % tensor-pipe
 // occupancy = the cuBLAS level; the pair only adds cross-SM latency per instruction) -> pairs serve 64->256 only.
@@ -220,7 +221,7 @@ cudaError_t launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
                         const CUtensorMap& b_lo, const dd::ConvArgs& args, int sm_count, cudaStream_t st) {
   using C = dd::HaloCfg<CIN, COUT, BK>;
   int grid = args.num_tiles < sm_count ? args.num_tiles : sm_count;
-  dd::conv3x3_halo_kernel<CIN, COUT, BK, EPI><<<grid, 256, C::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, args);
+  dd::conv3x3_halo_kernel<CIN, COUT, BK, EPI><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, args);
   return cudaGetLastError();
 }
 // CTA-pair variant (cluster of 2, tcgen05 cta_group::2) of the halo kernel for the 256-wide layers
@@ -231,7 +232,7 @@ cudaError_t launch_pair(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const 
   int grid = ((args.num_tiles + 1) & ~1) < (sm_count & ~1) ? ((args.num_tiles + 1) & ~1) : (sm_count & ~1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -549,7 +550,7 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
   a.out_lo = out_lo;
   a.split_scale = kActScale;
   a.status = e->status;
-  a.fp8_probe = getenv("DD_FP8_PROBE") ? 1 : 0;
+  a.fp8_probe = getenv("DD_FP8_PROBE") ? atoi(getenv("DD_FP8_PROBE")) : 0;
   a.clk_probe = e->clk_probe;
   cudaError_t err = cudaSuccess;
   e->launches++;
