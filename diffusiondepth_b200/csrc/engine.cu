@@ -156,6 +156,8 @@ cudaError_t configure_umma_all_epi() {
 }
 cudaError_t configure_all_kernels() {
   cudaError_t e;
+  if ((e = cudaFuncSetAttribute(dd::gn_apply_up_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::UPK_SMEM)) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<16, 64, 16>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<64, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<256, 256, 32>()) != cudaSuccess) return e;
@@ -710,9 +712,10 @@ int run_apply(dd_engine* e, int which, const float* temb, int temb_bstride, __ha
   a.scale = kActScale;
   a.status = e->status;
   // the tiled bilinear kernel needs the 32-pixel segment's source span to fit its 18-column staging buffer
-  if (COND == 2 && C == 256 && a.rx * 31.f + 2.f <= 18.f) {
-    dim3 grid((g.w + 31) / 32, g.h, g.B);
-    dd::gn_apply_up_split_kernel<<<grid, 256, 0, st>>>(a);
+  // (and two consecutive output rows to touch at most three source rows: ry <= 1)
+  if (COND == 2 && C == 256 && a.rx * 31.f + 2.f <= 18.f && a.ry <= 1.f) {
+    dim3 grid((g.w + 31) / 32, (g.h + 1) / 2, g.B);
+    dd::gn_apply_up_split_kernel<<<grid, 256, dd::UPK_SMEM, st>>>(a);
   } else {
     constexpr int PPB = 256 / (C / 8);
     dim3 grid((g.P + PPB - 1) / PPB, g.B);

@@ -5,6 +5,8 @@
 #pragma once
 #include "conv_umma.cuh"
 
+#include "ptx.cuh"
+
 namespace dd {
 
 __device__ __forceinline__ void split_f16(float v, float scale, __half& hi, __half& lo, bool& overflow) {
@@ -237,28 +239,44 @@ __global__ void __launch_bounds__(256) gn_apply_split_kernel(const ApplyArgs a) 
 }
 
 // Swin-head variant of the above for C = 256 with the bilinear (align_corners=True) condition injection, tiled:
-// one block = 32 consecutive output pixels of one latent row; the <= 2 x 18 source pixels of (cond + temb) they
-// interpolate from are staged in shared memory once (coalesced), instead of 4 gathered taps per output pixel.
+// one block = 32 consecutive output pixels of TWO consecutive latent rows.  The <= 3 x 18 source pixels of the
+// condition map they interpolate from are contiguous 18 KB runs in NHWC: one cp.async.bulk per source row stages them
+// in shared memory (no registers, no per-thread gather loop - a 36-iteration staging loop made the previous version
+// latency-bound at 35 % of HBM bandwidth), while the threads already stream their conv outputs.  The time embedding is
+// constant over space and the bilinear weights sum to one, so it is added after the interpolation.
+constexpr int UPK_SEG = 32, UPK_SW = 18, UPK_ROWS = 3;
+constexpr int UPK_SMEM = UPK_ROWS * UPK_SW * 256 * 4 + 2 * 256 * 4 + 16;
 __global__ void __launch_bounds__(256) gn_apply_up_split_kernel(const ApplyArgs a) {
-  constexpr int C = 256, SEG = 32, SW = 18;
-  __shared__ float sa[C], sb[C];
-  __shared__ __align__(16) float sc[2][SW][C];
-  const int b = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * SEG;
+  constexpr int C = 256, SEG = UPK_SEG, SW = UPK_SW;
+  extern __shared__ __align__(128) uint8_t upk_smem[];
+  float* sc = reinterpret_cast<float*>(upk_smem);                       // [3][SW][C]
+  float* sa = sc + UPK_ROWS * SW * C;
+  float* sb = sa + C;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + C);
+  const int b = blockIdx.z, oy0 = blockIdx.y * 2, ox0 = blockIdx.x * SEG;
   const int P = a.H * a.W;
   const int c0 = (threadIdx.x & 31) * 8;
-  // all of this thread's conv-output loads are issued first (8 x 16 B in flight per thread) so that they overlap the
-  // staging of the condition rows below: the kernel is a pure HBM stream (438 MB in, 438 MB out at C3)
-  float4 u[SEG / 8][2];
-#pragma unroll
-  for (int k = 0; k < SEG / 8; ++k) {
-    const int ox = ox0 + (threadIdx.x >> 5) + 8 * k;
-    if (ox < a.W) {
-      const size_t off = (static_cast<size_t>(b) * P + static_cast<size_t>(oy) * a.W + ox) * C + c0;
-      u[k][0] = __ldcs(reinterpret_cast<const float4*>(a.y + off));
-      u[k][1] = __ldcs(reinterpret_cast<const float4*>(a.y + off + 4));
-    } else {
-      u[k][0] = u[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  const int xs = static_cast<int>(a.rx * ox0);                          // first source column of this segment
+  const int ybase = static_cast<int>(a.ry * oy0);                       // first source row
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_proxy_async();
+    const int npx = min(SW, a.cw - xs);
+    const int nrow = min(UPK_ROWS, a.ch - ybase);
+    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nrow * npx * C * 4));
+    const float* base = a.cond + (static_cast<size_t>(b) * a.ch * a.cw) * C;
+    for (int r = 0; r < nrow; ++r)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(sc + r * SW * C)),
+                   "l"(reinterpret_cast<uint64_t>(base + (static_cast<size_t>(ybase + r) * a.cw + xs) * C)),
+                   "r"(static_cast<uint32_t>(npx * C * 4)), "r"(smem_u32(bar))
+                   : "memory");
+  }
+  float te[8];
+  {
+    const float4 t0 = *reinterpret_cast<const float4*>(a.temb + static_cast<size_t>(b) * a.temb_bstride + c0);
+    const float4 t1 = *reinterpret_cast<const float4*>(a.temb + static_cast<size_t>(b) * a.temb_bstride + c0 + 4);
+    te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
   }
   {
     const int c = threadIdx.x;
@@ -268,45 +286,60 @@ __global__ void __launch_bounds__(256) gn_apply_up_split_kernel(const ApplyArgs 
     sa[c] = scl;
     sb[c] = a.beta[c] - scl * mean;
   }
-  const float fy = a.ry * oy;
-  const int y0 = static_cast<int>(fy);
-  const int y1 = y0 + (y0 < a.ch - 1 ? 1 : 0);
-  const float ly1 = fy - y0, ly0 = 1.f - ly1;
-  const int xs = static_cast<int>(a.rx * ox0);  // first source column of this segment
-  {
-    const float te = a.temb[static_cast<size_t>(b) * a.temb_bstride + threadIdx.x];
-    const float* base = a.cond + static_cast<size_t>(b) * a.ch * a.cw * C;
-#pragma unroll 6
-    for (int i = 0; i < 2 * SW; ++i) {
-      const int rr = i / SW, cc = i % SW;
-      const int sx = min(xs + cc, a.cw - 1);
-      sc[rr][cc][threadIdx.x] = base[(static_cast<size_t>(rr ? y1 : y0) * a.cw + sx) * C + threadIdx.x] + te;
-    }
-  }
-  __syncthreads();
+  __syncthreads();  // sa / sb, and the barrier init is visible to the waiters
   bool ov = false;
+  bool staged = false;
+#pragma unroll 1
+  for (int rr = 0; rr < 2; ++rr) {
+    const int oy = oy0 + rr;
+    if (oy >= a.H) break;
+    // this thread's conv outputs of the row: 4 pixels x 8 channels, all loads in flight before the first use
+    float4 u[SEG / 8][2];
 #pragma unroll
-  for (int k = 0; k < SEG / 8; ++k) {
-    const int ox = ox0 + (threadIdx.x >> 5) + 8 * k;
-    if (ox >= a.W) continue;
-    const size_t off = (static_cast<size_t>(b) * P + static_cast<size_t>(oy) * a.W + ox) * C + c0;
-    const float v[8] = {u[k][0].x, u[k][0].y, u[k][0].z, u[k][0].w, u[k][1].x, u[k][1].y, u[k][1].z, u[k][1].w};
-    const float fx = a.rx * ox;
-    const int x0 = static_cast<int>(fx);
-    const int x1 = x0 + (x0 < a.cw - 1 ? 1 : 0);
-    const float lx1 = fx - x0, lx0 = 1.f - lx1;
-    const int i0 = x0 - xs, i1 = x1 - xs;
-    __align__(16) __half h[8];
-    __align__(16) __half l[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gn = fmaxf(fmaf(v[j], sa[c0 + j], sb[c0 + j]), 0.f);
-      const float up = ly0 * (lx0 * sc[0][i0][c0 + j] + lx1 * sc[0][i1][c0 + j]) +
-                       ly1 * (lx0 * sc[1][i0][c0 + j] + lx1 * sc[1][i1][c0 + j]);
-      split_f16(up + gn, a.scale, h[j], l[j], ov);
+    for (int k = 0; k < SEG / 8; ++k) {
+      const int ox = ox0 + (threadIdx.x >> 5) + 8 * k;
+      if (ox < a.W) {
+        const size_t off = (static_cast<size_t>(b) * P + static_cast<size_t>(oy) * a.W + ox) * C + c0;
+        u[k][0] = __ldcs(reinterpret_cast<const float4*>(a.y + off));
+        u[k][1] = __ldcs(reinterpret_cast<const float4*>(a.y + off + 4));
+      } else {
+        u[k][0] = u[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-    *reinterpret_cast<uint4*>(a.out_hi + off) = *reinterpret_cast<const uint4*>(h);
-    *reinterpret_cast<uint4*>(a.out_lo + off) = *reinterpret_cast<const uint4*>(l);
+    if (!staged) {
+      mbar_wait(bar, 0);
+      staged = true;
+    }
+    const float fy = a.ry * oy;
+    const int y0 = static_cast<int>(fy);
+    const int y1 = y0 + (y0 < a.ch - 1 ? 1 : 0);
+    const float ly1 = fy - y0, ly0 = 1.f - ly1;
+    const float* r0 = sc + (y0 - ybase) * SW * C;
+    const float* r1 = sc + (y1 - ybase) * SW * C;
+#pragma unroll
+    for (int k = 0; k < SEG / 8; ++k) {
+      const int ox = ox0 + (threadIdx.x >> 5) + 8 * k;
+      if (ox >= a.W) continue;
+      const size_t off = (static_cast<size_t>(b) * P + static_cast<size_t>(oy) * a.W + ox) * C + c0;
+      const float v[8] = {u[k][0].x, u[k][0].y, u[k][0].z, u[k][0].w, u[k][1].x, u[k][1].y, u[k][1].z, u[k][1].w};
+      const float fx = a.rx * ox;
+      const int x0 = static_cast<int>(fx);
+      const int x1 = x0 + (x0 < a.cw - 1 ? 1 : 0);
+      const float lx1 = fx - x0, lx0 = 1.f - lx1;
+      const int i0 = (x0 - xs) * C + c0, i1 = (x1 - xs) * C + c0;
+      __align__(16) __half h[8];
+      __align__(16) __half l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gn = fmaxf(fmaf(v[j], sa[c0 + j], sb[c0 + j]), 0.f);
+        // (cond + te) interpolated exactly as the reference does it: te enters every tap
+        const float up = ly0 * (lx0 * (r0[i0 + j] + te[j]) + lx1 * (r0[i1 + j] + te[j])) +
+                         ly1 * (lx0 * (r1[i0 + j] + te[j]) + lx1 * (r1[i1 + j] + te[j]));
+        split_f16(up + gn, a.scale, h[j], l[j], ov);
+      }
+      *reinterpret_cast<uint4*>(a.out_hi + off) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(a.out_lo + off) = *reinterpret_cast<const uint4*>(l);
+    }
   }
   if (ov) atomicOr(a.status, 1);
 }
