@@ -402,22 +402,26 @@ __global__ void pack_gen_weight_kernel(const float* __restrict__ w, const float*
     lo[o] = __float2half_rn(s - __half2float(h));
   }
 }
-// max |w * ch_scale[co]| for the power-of-two weight scale
+// max |w * ch_scale[co]| for the power-of-two weight scale (*out zeroed before the launch; see absmax_kernel)
 __global__ void absmax_scaled_kernel(const float* __restrict__ w, const float* __restrict__ ch_scale, int n, int per_co,
                                      int co_mod, int transposed, float* __restrict__ out) {
   __shared__ float sm[256];
   float m = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int co = transposed ? (i / 4) % co_mod : i / per_co;
-    m = fmaxf(m, fabsf(w[i] * (ch_scale ? ch_scale[co] : 1.f)));
+    const float v = fabsf(w[i] * (ch_scale ? ch_scale[co] : 1.f));
+    m = (v > m || v != v) ? v : m;
   }
   sm[threadIdx.x] = m;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + s]);
+    if (threadIdx.x < s) {
+      const float o = sm[threadIdx.x + s];
+      if (o > sm[threadIdx.x] || o != o) sm[threadIdx.x] = o;
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = sm[0];
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(sm[0]));
 }
 
 }  // namespace dd

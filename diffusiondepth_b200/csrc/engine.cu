@@ -51,6 +51,11 @@ int load_driver() {
   return DD_OK;
 }
 
+int absmax_grid(size_t n) {  // blocks of 256 threads, ~4 elements per thread, at most two per SM
+  const size_t b = (n + 1023) / 1024;
+  return static_cast<int>(b < 1 ? 1 : (b > 296 ? 296 : b));
+}
+
 CUtensorMapSwizzle swizzle_for(int bk) {
   return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
@@ -862,7 +867,8 @@ int pack_layer(dd_engine* e, ConvLayer& L, const float* w, const float* b, int c
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_lo), n * 2))) return rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_simt), n * 4))) return rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.bias), cout * 4))) return rc;
-  dd::absmax_kernel<<<1, 256, 0, st>>>(w, static_cast<int>(n), scratch_dev);
+  CUDA_TRY(cudaMemsetAsync(scratch_dev, 0, 4, st));
+  dd::absmax_kernel<<<absmax_grid(n), 256, 0, st>>>(w, static_cast<int>(n), scratch_dev);
   float amax = 0.f;
   CUDA_TRY(cudaMemcpyAsync(&amax, scratch_dev, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -961,7 +967,8 @@ int pack_gen(dd_engine* e, GenLayer& L, const std::string& wkey, const std::stri
   for (int i = 0; i < L.cout; ++i) shift_full[i] = shift[i % cout_conv];
   CUDA_TRY(cudaMemcpyAsync(L.shift, shift_full.data(), L.cout * 4, cudaMemcpyHostToDevice, st));
   const int nraw = static_cast<int>(static_cast<size_t>(cout_conv) * cin * (transposed ? 4 : taps));
-  dd::absmax_scaled_kernel<<<1, 256, 0, st>>>(w->ptr, d_scale, nraw, cin * taps, cout_conv, transposed ? 1 : 0, scratch);
+  CUDA_TRY(cudaMemsetAsync(scratch, 0, 4, st));
+  dd::absmax_scaled_kernel<<<absmax_grid(nraw), 256, 0, st>>>(w->ptr, d_scale, nraw, cin * taps, cout_conv, transposed ? 1 : 0, scratch);
   float amax = 0.f;
   CUDA_TRY(cudaMemcpyAsync(&amax, scratch, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -1185,7 +1192,8 @@ int pack_gemm(dd_engine* e, Gemm& G, const std::string& wkey, const std::string&
   } else {
     CUDA_TRY(cudaMemsetAsync(G.bias, 0, N * 4, st));
   }
-  dd::absmax_kernel<<<1, 256, 0, st>>>(w->ptr, static_cast<int>(n), scratch);
+  CUDA_TRY(cudaMemsetAsync(scratch, 0, 4, st));
+  dd::absmax_kernel<<<absmax_grid(n), 256, 0, st>>>(w->ptr, static_cast<int>(n), scratch);
   float amax = 0.f;
   CUDA_TRY(cudaMemcpyAsync(&amax, scratch, 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -2006,8 +2014,8 @@ int dd_conv3x3(dd_handle h, const float* x, const float* w, const float* b, floa
   int rc;
   if ((rc = transpose_in(x, xn, batch, cin, height * width, st))) return rc;
   float* amax_dev = reinterpret_cast<float*>(status) + 8;
-  dd::absmax_kernel<<<1, 256, 0, st>>>(xn, static_cast<int>(std::min<size_t>(BP * cin, 1u << 30)), amax_dev);
-  dd::absmax_kernel<<<1, 256, 0, st>>>(w, static_cast<int>(nw), amax_dev + 1);
+  dd::absmax_kernel<<<absmax_grid(BP * cin), 256, 0, st>>>(xn, static_cast<int>(std::min<size_t>(BP * cin, 1u << 30)), amax_dev);  // zeroed with status
+  dd::absmax_kernel<<<absmax_grid(nw), 256, 0, st>>>(w, static_cast<int>(nw), amax_dev + 1);
   float am[2] = {0.f, 0.f};
   CUDA_TRY(cudaMemcpyAsync(am, amax_dev, 8, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));

@@ -86,17 +86,25 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __r
     w_simt[(static_cast<size_t>(tap) * cin + ci) * cout + co] = v;
   }
 }
+// max |w| over n elements.  *out must be zeroed before the launch; any grid size: blocks combine through an integer
+// atomicMax on the bit pattern (non-negative floats order like unsigned ints; NaN sorts above inf, so it still surfaces).
 __global__ void absmax_kernel(const float* __restrict__ w, int n, float* __restrict__ out) {
   __shared__ float sm[256];
   float m = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float v = fabsf(w[i]);
+    m = (v > m || v != v) ? v : m;
+  }
   sm[threadIdx.x] = m;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + s]);
+    if (threadIdx.x < s) {
+      const float o = sm[threadIdx.x + s];
+      if (o > sm[threadIdx.x] || o != o) sm[threadIdx.x] = o;
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = sm[0];
+  if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(sm[0]));
 }
 
 // ------------------------------------------------------------------ GroupNorm(4, C) finalize
