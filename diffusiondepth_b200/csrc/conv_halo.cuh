@@ -212,7 +212,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint32_t sa_lo = sa_hi + C::STRIP_PAD;
           const uint32_t sb_hi = smem_u32(b_ring + sb * C::B_SLOT);
           const uint32_t sb_lo = sb_hi + C::B_TILE_PAD;
-          if (!PAIR && p.fp8_probe == 1) {
+          if (!PAIR && p.fp8_probe == 3) {
+            // DESIGN probe (DD_FP8_PROBE=3): the intrinsic rate of kind::f8f6f4 — three K = 32 e4m3 MMAs per chunk and
+            // nothing else (same operand bytes as one fp16 pass pair; results are garbage)
+            constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) | (static_cast<uint32_t>(TILE_M >> 4) << 24);
+            umma_f8(d_tmem, umma_smem_desc(sa_hi, C::ROW_BYTES), umma_smem_desc(sb_hi, C::ROW_BYTES), idesc8, (kc | tap) != 0 ? 1u : 0u);
+            umma_f8(d_tmem, umma_smem_desc(sa_lo, C::ROW_BYTES), umma_smem_desc(sb_hi, C::ROW_BYTES), idesc8, 1u);
+            umma_f8(d_tmem, umma_smem_desc(sa_hi, C::ROW_BYTES), umma_smem_desc(sb_lo, C::ROW_BYTES), idesc8, 1u);
+          } else if (!PAIR && p.fp8_probe == 1) {
             // DESIGN probe (DD_FP8_PROBE=1): fp16 hi*hi (2 x K16) + the two correction products as ONE e4m3 MMA each
             // (K = 32): 4 instructions per chunk instead of 6.  Operand bytes are reinterpreted, results are garbage.
             constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) | (static_cast<uint32_t>(TILE_M >> 4) << 24);

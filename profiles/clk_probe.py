@@ -7,8 +7,8 @@ from diffusiondepth_b200.model.registry import HEADS
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
 head = HEADS.build(dict(type="DDIMDepthEstimate_Swin_ADDHAHI", in_channels=[64,128,256,512], inference_steps=20, num_train_timesteps=1000, depth_feature_dim=16, loss_cfgs=[], init_cfg=None)).eval().to(dev)
-for pair, fp8 in ((False, False), (True, False), (False, True)):
-    if fp8: os.environ["DD_FP8_PROBE"] = "1"
+for pair, fp8 in ((False, 0), (True, 0), (False, 1), (False, 3)):
+    if fp8: os.environ["DD_FP8_PROBE"] = str(fp8)
     e = dd.DenoiseEngine("swin", 4, (176, 608), (88, 304), 20, dev, cuda_graph=False, pair_wide=pair)
     e.load_weights(head._engine_tensors()); e.set_schedule(*head.scheduler.fused_coefficients(20))
     for cin, cout in [(64, 256), (256, 256)]:
