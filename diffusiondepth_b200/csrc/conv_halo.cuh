@@ -41,12 +41,17 @@ struct HaloCfg {
   static constexpr int B_TILE = B_ROWS * ROW_BYTES;                 // one plane, one tap, one chunk
   static constexpr int B_TILE_PAD = (B_TILE + 1023) / 1024 * 1024;
   static constexpr int B_SLOT = 2 * B_TILE_PAD;
-  static constexpr int A_SLOTS = PAIR ? 3 : 2;
-  static constexpr int EPI_SETS = (COUT == 64) ? 2 : 1;  // as ConvCfg: Cout = 64 drains its two 32-channel chunks in parallel
+  static constexpr int A_SLOTS = 2;
+  // Two sets of four epilogue warps where the epilogue is on the critical path: Cout = 64 (two chunks, one per set; each
+  // set then owns two GroupNorm groups) and the pair kernel's 64->256 layer (K = 576: 18 stages per tile, so draining a
+  // 128 x 256 fp32 tile with one warp per scheduler took as long as the mainloop; the sets take alternate chunks and
+  // each holds partial sums of all four groups).
+  static constexpr int EPI_SETS = (COUT == 64 || PAIR) ? 2 : 1;
+  static constexpr bool STATS_LOCAL = (COUT == 64);  // a set's chunk(s) cover whole groups of their own
   static constexpr int EPI_WARPS = 4 * EPI_SETS;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;
-  static constexpr int BUDGET = 227 * 1024 - 1024 - 512 - XPOSE_BYTES - A_SLOTS * A_SLOT;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 1024 - XPOSE_BYTES - A_SLOTS * A_SLOT;
   static constexpr int B_SLOTS_RAW = BUDGET / B_SLOT;
   // Small layers (16->64, 64->16): all 9 x KC weight tiles fit in shared memory -> fetch them ONCE per CTA instead of once
   // per tile.  Each cp.async.bulk.tensor costs its issuing thread ~160 ns, and 18 weight copies per 128-pixel tile were
@@ -54,7 +59,7 @@ struct HaloCfg {
   static constexpr bool B_RESIDENT = !PAIR && (9 * KC * B_SLOT <= 40 * 1024) && (9 * KC <= B_SLOTS_RAW);
   static constexpr int B_SLOTS = B_RESIDENT ? 9 * KC : (B_SLOTS_RAW > 8 ? 8 : B_SLOTS_RAW);
   static_assert(B_SLOTS >= 2, "B ring too small");
-  static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 512 + XPOSE_BYTES;
+  static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 1024 + XPOSE_BYTES;
   static constexpr int A_TX = 6 * STRIP_BYTES;
   static constexpr int B_TX = 2 * B_TILE;
   // Narrow-N layers: back-to-back MMAs into ONE accumulator serialise on its read-modify-write latency (~105 cycles
@@ -88,7 +93,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [2][4][4][2]
-  float* xpose = reinterpret_cast<float*>(ctrl + 512);
+  float* xpose = reinterpret_cast<float*>(ctrl + 1024);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -114,7 +119,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], PAIR ? 8 : C::EPI_WARPS);
+      mbar_init(&tempty_bar[b], PAIR ? 2 * C::EPI_WARPS : C::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -278,7 +283,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int q = warp & 3;
     const int es = (warp - 4) >> 2;  // epilogue set (see ConvCfg::EPI_SETS)
     constexpr int NCH = COUT / C::CH;
-    static_assert(C::EPI_SETS == 1 || NCH == C::EPI_SETS, "one chunk per set");
+    static_assert(NCH % C::EPI_SETS == 0 && (C::EPI_SETS == 1 || C::STATS_LOCAL || C::GROUP_CH % (C::EPI_SETS * C::CH) == 0),
+                  "chunks split evenly over the sets; a set's chunk never straddles a GroupNorm group");
     const int m = q * 32 + lane;
     const int r = m >> 3, c = m & 7;
     uint32_t full_phase = 0;
@@ -335,7 +341,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           if (valid) {
 #pragma unroll
             for (int j = 0; j < C::CH; ++j) {
-              const int g = C::EPI_SETS == 1 ? (cj * C::CH + j) / C::GROUP_CH : j / C::GROUP_CH;
+              // compile-time: chunk cj * SETS + es lies in group cj * SETS * CH / GROUP_CH for either es, except for
+              // Cout = 64 where the set's single chunk holds its own two groups (local index)
+              const int g = C::STATS_LOCAL ? j / C::GROUP_CH : (cj * C::EPI_SETS * C::CH + j) / C::GROUP_CH;
               tsum[g] += v[j];
               tsq[g] = fmaf(v[j], v[j], tsq[g]);
             }
@@ -394,9 +402,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           }
           if (lane == 0) {
-            if constexpr (C::EPI_SETS == 1) {
-              red[((par * 4 + q) * 4 + g) * 2 + 0] = s;
-              red[((par * 4 + q) * 4 + g) * 2 + 1] = s2;
+            if constexpr (!C::STATS_LOCAL) {  // every epilogue warp has a partial sum of every group
+              red[((par * C::EPI_WARPS + es * 4 + q) * 4 + g) * 2 + 0] = s;
+              red[((par * C::EPI_WARPS + es * 4 + q) * 4 + g) * 2 + 1] = s2;
             } else if (g < 2) {
               red[((par * 8 + es * 4 + q) * 2 + g) * 2 + 0] = s;
               red[((par * 8 + es * 4 + q) * 2 + g) * 2 + 1] = s2;
@@ -409,10 +417,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         if (e < 8 && tile < p.num_tiles) {
           const int g = e >> 1, which = e & 1;
           float t = 0.f;
+          if constexpr (!C::STATS_LOCAL) {
 #pragma unroll
-          for (int w = 0; w < 4; ++w)
-            t += C::EPI_SETS == 1 ? red[((par * 4 + w) * 4 + g) * 2 + which]
-                                  : red[((par * 8 + (g >> 1) * 4 + w) * 2 + (g & 1)) * 2 + which];
+            for (int w = 0; w < C::EPI_WARPS; ++w) t += red[((par * C::EPI_WARPS + w) * 4 + g) * 2 + which];
+          } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) t += red[((par * 8 + (g >> 1) * 4 + w) * 2 + (g & 1)) * 2 + which];
+          }
           p.stats_partial[(static_cast<size_t>(tile) * 4 + g) * 2 + which] = t;
         }
         par ^= 1;
