@@ -399,3 +399,55 @@ def test_host_buffer_end_to_end_call():
     z_ref = torch.from_numpy(g["z"]["logits"])
     rel = (pred - ref).abs() / ref.abs().clamp_min(1e-6)
     assert rel[(z_ref < 6) & (z_ref > -13)].max().item() < TOL
+
+
+def test_one_step_loop_equals_operator_plus_update_plus_decode():
+    """Size-independent property tying the three C-ABI entry points together: a T = 1 `dd_denoise_decode` must equal
+    eps = `dd_denoiser_forward`(x_T, t_0) -> x_0 = c_x x_T + c_eps eps -> `dd_decode`(x_0), and depth = exp(-z)
+    where it is well conditioned."""
+    head = _swin_head(1).to(DEV)
+    g = torch.Generator().manual_seed(11)
+    B, (h, w) = 2, (24, 40)
+    cond = torch.randn(B, 256, 12, 20, generator=g).abs().to(DEV)
+    noise = torch.randn(B, 16, h, w, generator=g).to(DEV)
+    eng = head._engine(B, (h, w), (12, 20), DEV)
+    depth, latent, z = eng.denoise_decode(cond, noise, want_latent=True, want_logits=True)
+    ts, cx, ce = head.scheduler.fused_coefficients(1)
+    eps = eng.denoiser_forward(cond, noise, int(ts[0]))
+    x0 = (cx[0] * noise.double() + ce[0] * eps.double()).float()
+    assert (x0 - latent).abs().max().item() < 2e-5 * max(1.0, latent.abs().max().item())
+    depth2, z2 = eng.decode(latent, want_logits=True)
+    assert torch.equal(depth2, depth) and torch.equal(z2, z)
+    well = (z < 6) & (z > -13)
+    assert ((depth - torch.exp(-z)).abs() / torch.exp(-z))[well].max().item() < 1e-3
+    eng.poll_status()
+
+
+def test_cabi_rejects_bad_arguments_with_status_codes():
+    """Error behaviour of the boundary: int status + dd_last_error(), never a crash or a silent fallback."""
+    import ctypes as C
+    from diffusiondepth_b200 import _cabi
+    lib = _cabi.load_library()
+    h = C.c_void_p()
+    bad = _cabi.DDConfig(_cabi.ABI_VERSION + 7, _cabi.VARIANT_SWIN, 1, 8, 16, 4, 8, 2, 0, 0)
+    assert lib.dd_create(C.byref(bad), C.byref(h)) != 0 and b"abi" in lib.dd_last_error().lower()
+    res_mismatch = _cabi.DDConfig(_cabi.ABI_VERSION, _cabi.VARIANT_RES, 1, 8, 16, 4, 8, 2, 0, 0)
+    assert lib.dd_create(C.byref(res_mismatch), C.byref(h)) != 0  # Res heads condition at latent resolution
+    eng = dd.DenoiseEngine("swin", 1, (8, 16), (4, 8), 2, DEV, cuda_graph=False)
+    noise = torch.zeros(1, 16, 8, 16, device=DEV)
+    cond = torch.zeros(1, 256, 4, 8, device=DEV)
+    with pytest.raises(dd.EngineError):  # weights never registered
+        eng.denoise_decode(cond, noise)
+    with pytest.raises(dd.EngineError):  # wrong shape is refused on the host side
+        eng.denoise_decode(cond, torch.zeros(1, 16, 8, 17, device=DEV))
+    head = _swin_head(2).to(DEV)
+    eng.load_weights(head._engine_tensors())
+    eng.set_schedule(*head.scheduler.fused_coefficients(2))
+    depth = torch.empty(1, 1, 16, 32, device=DEV)
+    small = torch.empty(4096, dtype=torch.uint8, device=DEV)
+    rc = lib.dd_denoise_decode(eng._h, C.c_void_p(cond.data_ptr()), C.c_void_p(noise.data_ptr()), C.c_void_p(0),
+                               C.c_void_p(0), C.c_void_p(depth.data_ptr()), C.c_void_p(small.data_ptr()), 4096,
+                               C.c_void_p(0))
+    assert rc != 0 and b"workspace" in lib.dd_last_error().lower()
+    assert eng.denoise_decode(cond, noise)[0].shape == (1, 1, 16, 32)  # the handle is still usable afterwards
+    eng.close()
