@@ -196,8 +196,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
-    // ------------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only).
+    // The WHOLE warp walks the loop (barrier waits, operand addresses: warp-uniform, so the compiler keeps them in
+    // uniform registers) and one elected lane issues the MMAs and commits.  With a lone `lane == 0` thread in a
+    // divergent region every tcgen05.mma was wrapped in an elect/branch loop with R2UR moves (~16 SASS instructions per
+    // MMA), and the issue stream, not the tensor pipe, set the pace.
+    const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, COUT);
     int sa = 0, sb = 0, buf = 0;
     uint32_t pa = 0, pb = 0, acc_phase = 0;
@@ -217,6 +222,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint32_t sa_lo = sa_hi + C::STRIP_PAD;
           const uint32_t sb_hi = smem_u32(b_ring + sb * C::B_SLOT);
           const uint32_t sb_lo = sb_hi + C::B_TILE_PAD;
+          if (leader) {
+#ifdef DD_PROBES  // timing probes of DESIGN.md §8 / profiles/README.md (build with -DDD_PROBES)
           if (!PAIR && p.fp8_probe == 3) {
             // DESIGN probe (DD_FP8_PROBE=3): the intrinsic rate of kind::f8f6f4 — three K = 32 e4m3 MMAs per chunk and
             // nothing else (same operand bytes as one fp16 pass pair; results are garbage)
@@ -234,7 +241,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                        (kc | tap | k) != 0 ? 1u : 0u);
             umma_f8(d_tmem, umma_smem_desc(sa_lo, C::ROW_BYTES), umma_smem_desc(sb_hi, C::ROW_BYTES), idesc8, 1u);
             umma_f8(d_tmem, umma_smem_desc(sa_hi, C::ROW_BYTES), umma_smem_desc(sb_lo, C::ROW_BYTES), idesc8, 1u);
-          } else
+          }
+          else
+#endif
 #pragma unroll
           for (int k = 0; k < C::KSTEPS; ++k) {
             const uint64_t a_hi = umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES);
@@ -242,34 +251,48 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
             const uint64_t b_lo = umma_smem_desc(sb_lo + k * 32, C::ROW_BYTES);
             const uint32_t first = (kc | tap | k) != 0 ? 1u : 0u;
+            // order: neighbours share an operand (B_hi between the first two, A_hi between the last two); measured
+            // neutral against lo*hi, hi*lo, hi*hi (a 5 % difference seen in the ordering probe followed the code path of
+            // the issuing thread, not the order)
             if constexpr (C::NACC == 3) {
               umma_f16(d_tmem, a_lo, b_hi, idesc, first);
-              umma_f16(d_tmem + COUT, a_hi, b_lo, idesc, first);
               umma_f16(d_tmem + 2 * COUT, a_hi, b_hi, idesc, first);
+              umma_f16(d_tmem + COUT, a_hi, b_lo, idesc, first);
             } else if constexpr (PAIR) {
               umma_f16_pair(d_tmem, a_lo, b_hi, idesc, first);
-              umma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1u);
               umma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1u);
-            } else {
+              umma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1u);
+#ifdef DD_PROBES
+            } else if (p.fp8_probe == 4) {  // ordering probe: the previous order
               umma_f16(d_tmem, a_lo, b_hi, idesc, first);
               umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
               umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+#endif
+            } else {
+              umma_f16(d_tmem, a_lo, b_hi, idesc, first);
+              umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+              umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
             }
           }
           if constexpr (PAIR) umma_commit_pair(&b_empty[sb], 3);
           else if constexpr (!C::B_RESIDENT) umma_commit(&b_empty[sb]);
+          }  // leader
+          __syncwarp();
           if (++sb == C::B_SLOTS) {
             sb = 0;
             pb ^= 1;
           }
         }
-        if constexpr (PAIR) {
-          umma_commit_pair(&a_empty[sa], 3);
-          if (kc == C::KC - 1) umma_commit_pair(&tfull_bar[buf], 3);
-        } else {
-          umma_commit(&a_empty[sa]);
-          if (kc == C::KC - 1) umma_commit(&tfull_bar[buf]);
+        if (leader) {
+          if constexpr (PAIR) {
+            umma_commit_pair(&a_empty[sa], 3);
+            if (kc == C::KC - 1) umma_commit_pair(&tfull_bar[buf], 3);
+          } else {
+            umma_commit(&a_empty[sa]);
+            if (kc == C::KC - 1) umma_commit(&tfull_bar[buf]);
+          }
         }
+        __syncwarp();
         if (++sa == C::A_SLOTS) {
           sa = 0;
           pa ^= 1;

@@ -109,8 +109,10 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: the whole warp walks the loop, one
+    // elected lane issues (uniform-register operands, back-to-back MMAs; see conv_halo.cuh)
+    const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(128, SWAP_N);
     int stage = 0, buf = 0;
     uint32_t phase = 0, acc_phase = 0;
@@ -124,6 +126,7 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
         const uint32_t sw = smem_u32(stage_ptr(stage));
         const uint32_t sp_hi = sw + C::W_BYTES;
         const uint32_t sp_lo = sp_hi + C::P_BYTES;
+        if (leader) {
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t wd = umma_smem_desc(sw + k * 32, C::ROW_BYTES);
@@ -134,6 +137,8 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
         }
         umma_commit(&empty_bar[stage]);
         if (it == C::K_ITERS - 1) umma_commit(&tfull_bar[buf]);
+        }  // leader
+        __syncwarp();
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;

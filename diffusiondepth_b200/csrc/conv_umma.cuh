@@ -164,8 +164,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: the whole warp walks the loop, one
+    // elected lane issues (uniform-register operands, back-to-back MMAs; see conv_halo.cuh)
+    const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(TILE_M, COUT);
     int stage = 0;
     uint32_t phase = 0;
@@ -182,6 +184,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const uint32_t sa_lo = sa_hi + C::A_BYTES;
         const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
         const uint32_t sb_lo = sb_hi + C::B_BYTES;
+        if (leader) {
 #pragma unroll
         for (int k = 0; k < C::KSTEPS; ++k) {
           const uint64_t a_hi = umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES);
@@ -189,18 +192,21 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
           const uint64_t b_lo = umma_smem_desc(sb_lo + k * 32, C::ROW_BYTES);
           const uint32_t first = (it | k) != 0 ? 1u : 0u;
+          // neighbours share an operand (B_hi, then A_hi); see conv_halo.cuh
           if constexpr (C::NACC == 3) {
             umma_f16(d_tmem, a_lo, b_hi, idesc, first);
-            umma_f16(d_tmem + COUT, a_hi, b_lo, idesc, first);
             umma_f16(d_tmem + 2 * COUT, a_hi, b_hi, idesc, first);
+            umma_f16(d_tmem + COUT, a_hi, b_lo, idesc, first);
           } else {
             umma_f16(d_tmem, a_lo, b_hi, idesc, first);
-            umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
             umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+            umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
           }
         }
         umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
         if (it == C::K_ITERS - 1) umma_commit(&tfull_bar[buf]);
+        }  // leader
+        __syncwarp();
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;

@@ -134,7 +134,10 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    // the whole warp walks the loop (waits and operand addresses stay warp-uniform -> uniform registers, MMAs issued
+    // back to back); one elected lane issues the MMAs and commits (see conv_halo.cuh)
+    const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc_f16(TILE_M, NT);
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
@@ -150,18 +153,22 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
         const uint32_t sa_lo = sa_hi + C::A_BYTES;
         const uint32_t sb_hi = sa_hi + 2 * C::A_BYTES;
         const uint32_t sb_lo = sb_hi + C::B_BYTES;
+        if (leader) {
 #pragma unroll
         for (int k = 0; k < C::BK / 16; ++k) {
           const uint64_t a_hi = umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES);
           const uint64_t a_lo = umma_smem_desc(sa_lo + k * 32, C::ROW_BYTES);
           const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
           const uint64_t b_lo = umma_smem_desc(sb_lo + k * 32, C::ROW_BYTES);
+          // neighbours share an operand (B_hi, then A_hi); see conv_halo.cuh
           umma_f16(d_tmem, a_lo, b_hi, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
           umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+          umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
         }
         umma_commit(&empty_bar[stage]);
         if (it == k_iters - 1) umma_commit(&tfull_bar[buf]);
+        }  // leader
+        __syncwarp();
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;

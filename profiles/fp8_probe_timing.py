@@ -1,4 +1,5 @@
-"""Timing-only probe: convA (256->256) with the two correction products issued as FP8 MMAs (DD_FP8_PROBE=1) vs the
+"""(The fp8 / ordering probe branches are compiled only with `DD_PROBES=1 python __graft_entry__.py --force`.)
+Timing-only probe: convA (256->256) with the two correction products issued as FP8 MMAs (DD_FP8_PROBE=1) vs the
 production 3 x fp16 sequence.  Results of the probe mode are garbage by construction; only the kernel time matters."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
