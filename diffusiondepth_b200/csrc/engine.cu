@@ -196,9 +196,10 @@ constexpr int kSwapBK[5] = {16, 0, 0, 32, 32};    // K chunk of the swapped-oper
 // through TMA zero fill was slower still, 110-125 us); row-halo reuse pays for the wide layers.
 constexpr bool kUseSwap[5] = {false, false, false, true, true};
 constexpr bool kUseHalo[5] = {true, true, true, false, false};
-// CTA pairs (cta_group::2) measured in cycles (profiles/clk_probe.py): 64->256 -6 % (its short K leaves the epilogue
-// exposed and halving the weight traffic through shared memory helps it), 256->256 +7 % (already at ~81 % tensor-pipe
-// occupancy = the cuBLAS level; the pair only adds cross-SM latency per instruction) -> pairs serve 64->256 only.
+// CTA pairs (cta_group::2), measured (profiles/README.md): 64->256 with two epilogue warp sets 250 us at 89 % tensor
+// pipe vs 362 us single-CTA (its short K leaves the epilogue exposed; the pair halves the weight traffic through shared
+// memory); 256->256 is equal within noise (already at ~81 % tensor-pipe occupancy = the cuBLAS level) -> pairs serve
+// 64->256 only.
 constexpr bool kUsePair[5] = {false, true, false, false, false};
 template <int CIN, int COUT, int BK, int EPI>
 cudaError_t launch_swap(const CUtensorMap& p_hi, const CUtensorMap& p_lo, const CUtensorMap& w, const dd::ConvArgs& args,
