@@ -28,6 +28,7 @@ WORKLOADS = {  # name -> (family, T, per-GPU batch, H, W, GFLOP per map: BASELIN
     "C3": ("swinl", 20, 4, 352, 1216, 7258.7),
     "C2": ("res50", 20, 8, 228, 304, 270.5),
     "C5": ("swinl", 50, 8, 480, 640, 12083.0),
+    "C1": ("res18", 5, 1, 228, 304, 86.8),  # BASELINE configs[0]: the reference's own CPU-runnable case (contract tests)
 }
 
 
