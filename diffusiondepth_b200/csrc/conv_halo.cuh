@@ -137,8 +137,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer (A strips)
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (A strips).  Like the MMA issuer
+    // below, the WHOLE warp walks the loop (barrier waits and coordinates stay warp-uniform) and one elected lane issues
+    // the copies: with a lone `lane == 0` thread in a divergent region every cp.async.bulk.tensor was wrapped in an
+    // ELECT / BRA.U.ANY loop (cuobjdump), now the six copies of a chunk are consecutive UTMALDGs.
+    const bool leader = elect_one();
     int sa = 0;
     uint32_t pa = 0;
     DD_TILE_LOOP {
@@ -147,30 +151,34 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       for (int kc = 0; kc < C::KC; ++kc) {
         mbar_wait(&a_empty[sa], pa ^ 1);
         uint8_t* s = a_ring + sa * C::A_SLOT;
-        if constexpr (PAIR) {
-          const uint32_t lead = mapa_u32(smem_u32(&a_full[sa]), 0);
-          mbar_arrive_expect_tx_cluster(lead, C::A_TX);
+        if (leader) {
+          if constexpr (PAIR) {
+            const uint32_t lead = mapa_u32(smem_u32(&a_full[sa]), 0);
+            mbar_arrive_expect_tx_cluster(lead, C::A_TX);
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            tma_load_4d_pair(s + (2 * dx) * C::STRIP_PAD, &tmA_hi, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
-            tma_load_4d_pair(s + (2 * dx + 1) * C::STRIP_PAD, &tmA_lo, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
-          }
-        } else {
-          mbar_arrive_expect_tx(&a_full[sa], C::A_TX);
+            for (int dx = 0; dx < 3; ++dx) {
+              tma_load_4d_pair(s + (2 * dx) * C::STRIP_PAD, &tmA_hi, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+              tma_load_4d_pair(s + (2 * dx + 1) * C::STRIP_PAD, &tmA_lo, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+            }
+          } else {
+            mbar_arrive_expect_tx(&a_full[sa], C::A_TX);
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            tma_load_4d(s + (2 * dx) * C::STRIP_PAD, &tmA_hi, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
-            tma_load_4d(s + (2 * dx + 1) * C::STRIP_PAD, &tmA_lo, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
+            for (int dx = 0; dx < 3; ++dx) {
+              tma_load_4d(s + (2 * dx) * C::STRIP_PAD, &tmA_hi, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
+              tma_load_4d(s + (2 * dx + 1) * C::STRIP_PAD, &tmA_lo, &a_full[sa], kc * BK, x0 + dx - 1, y0 - 1, img);
+            }
           }
         }
+        __syncwarp();
         if (++sa == C::A_SLOTS) {
           sa = 0;
           pa ^= 1;
         }
       }
     }
-  } else if (warp == 3 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer (B weight tiles)
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMA producer (B weight tiles), same structure
+    const bool leader = elect_one();
     int sb = 0;
     uint32_t pb = 0;
     DD_TILE_LOOP {
@@ -179,16 +187,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_empty[sb], pb ^ 1);
           uint8_t* s = b_ring + sb * C::B_SLOT;
-          if constexpr (PAIR) {  // this CTA's half of the output channels
-            const uint32_t lead = mapa_u32(smem_u32(&b_full[sb]), 0);
-            mbar_arrive_expect_tx_cluster(lead, C::B_TX);
-            tma_load_3d_pair(s, &tmB_hi, lead, kc * BK, static_cast<int>(rank) * C::B_ROWS, tap);
-            tma_load_3d_pair(s + C::B_TILE_PAD, &tmB_lo, lead, kc * BK, static_cast<int>(rank) * C::B_ROWS, tap);
-          } else {
-            mbar_arrive_expect_tx(&b_full[sb], C::B_TX);
-            tma_load_3d(s, &tmB_hi, &b_full[sb], kc * BK, 0, tap);
-            tma_load_3d(s + C::B_TILE_PAD, &tmB_lo, &b_full[sb], kc * BK, 0, tap);
+          if (leader) {
+            if constexpr (PAIR) {  // this CTA's half of the output channels
+              const uint32_t lead = mapa_u32(smem_u32(&b_full[sb]), 0);
+              mbar_arrive_expect_tx_cluster(lead, C::B_TX);
+              tma_load_3d_pair(s, &tmB_hi, lead, kc * BK, static_cast<int>(rank) * C::B_ROWS, tap);
+              tma_load_3d_pair(s + C::B_TILE_PAD, &tmB_lo, lead, kc * BK, static_cast<int>(rank) * C::B_ROWS, tap);
+            } else {
+              mbar_arrive_expect_tx(&b_full[sb], C::B_TX);
+              tma_load_3d(s, &tmB_hi, &b_full[sb], kc * BK, 0, tap);
+              tma_load_3d(s + C::B_TILE_PAD, &tmB_lo, &b_full[sb], kc * BK, 0, tap);
+            }
           }
+          __syncwarp();
           if (++sb == C::B_SLOTS) {
             sb = 0;
             pb ^= 1;
@@ -223,24 +234,44 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint32_t sb_hi = smem_u32(b_ring + sb * C::B_SLOT);
           const uint32_t sb_lo = sb_hi + C::B_TILE_PAD;
           if (leader) {
-#ifdef DD_PROBES  // timing probes of DESIGN.md §8 / profiles/README.md (build with -DDD_PROBES)
-          if (!PAIR && p.fp8_probe == 3) {
-            // DESIGN probe (DD_FP8_PROBE=3): the intrinsic rate of kind::f8f6f4 — three K = 32 e4m3 MMAs per chunk and
-            // nothing else (same operand bytes as one fp16 pass pair; results are garbage)
-            constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) | (static_cast<uint32_t>(TILE_M >> 4) << 24);
-            umma_f8(d_tmem, umma_smem_desc(sa_hi, C::ROW_BYTES), umma_smem_desc(sb_hi, C::ROW_BYTES), idesc8, (kc | tap) != 0 ? 1u : 0u);
-            umma_f8(d_tmem, umma_smem_desc(sa_lo, C::ROW_BYTES), umma_smem_desc(sb_hi, C::ROW_BYTES), idesc8, 1u);
-            umma_f8(d_tmem, umma_smem_desc(sa_hi, C::ROW_BYTES), umma_smem_desc(sb_lo, C::ROW_BYTES), idesc8, 1u);
-          } else if (!PAIR && p.fp8_probe == 1) {
-            // DESIGN probe (DD_FP8_PROBE=1): fp16 hi*hi (2 x K16) + the two correction products as ONE e4m3 MMA each
-            // (K = 32): 4 instructions per chunk instead of 6.  Operand bytes are reinterpreted, results are garbage.
-            constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) | (static_cast<uint32_t>(TILE_M >> 4) << 24);
+#ifdef DD_PROBES  // timing probes of DESIGN.md §8 / profiles/README.md (build with -DDD_PROBES); results are garbage
+          if (p.fp8_probe == 3 || p.fp8_probe == 1) {
+            // 3: the intrinsic rate of kind::f8f6f4 — three K = 32 e4m3 MMAs per (chunk, tap) stage and nothing else;
+            // 1: fp16 hi*hi (2 x K16) + the two correction products as ONE e4m3 K = 32 MMA each (4 instructions, not 6).
+            // Operand bytes are reinterpreted (the first 32 bytes of each 64-byte row = 32 e4m3 values).
+            constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) |
+                                        (static_cast<uint32_t>((PAIR ? 2 * TILE_M : TILE_M) >> 4) << 24);
+            const uint64_t d_ah = umma_smem_desc(sa_hi, C::ROW_BYTES), d_al = umma_smem_desc(sa_lo, C::ROW_BYTES);
+            const uint64_t d_bh = umma_smem_desc(sb_hi, C::ROW_BYTES), d_bl = umma_smem_desc(sb_lo, C::ROW_BYTES);
+            const uint32_t first = (kc | tap) != 0 ? 1u : 0u;
+            if (p.fp8_probe == 3) {
+              if constexpr (PAIR) {
+                umma_f8_pair(d_tmem, d_ah, d_bh, idesc8, first);
+                umma_f8_pair(d_tmem, d_al, d_bh, idesc8, 1u);
+                umma_f8_pair(d_tmem, d_ah, d_bl, idesc8, 1u);
+              } else {
+                umma_f8(d_tmem, d_ah, d_bh, idesc8, first);
+                umma_f8(d_tmem, d_al, d_bh, idesc8, 1u);
+                umma_f8(d_tmem, d_ah, d_bl, idesc8, 1u);
+              }
+            } else {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_f16(d_tmem, umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES), umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES), idesc,
-                       (kc | tap | k) != 0 ? 1u : 0u);
-            umma_f8(d_tmem, umma_smem_desc(sa_lo, C::ROW_BYTES), umma_smem_desc(sb_hi, C::ROW_BYTES), idesc8, 1u);
-            umma_f8(d_tmem, umma_smem_desc(sa_hi, C::ROW_BYTES), umma_smem_desc(sb_lo, C::ROW_BYTES), idesc8, 1u);
+              for (int k = 0; k < BK / 16; ++k) {
+                if constexpr (PAIR)
+                  umma_f16_pair(d_tmem, umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES), umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES), idesc,
+                                (kc | tap | k) != 0 ? 1u : 0u);
+                else
+                  umma_f16(d_tmem, umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES), umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES), idesc,
+                           (kc | tap | k) != 0 ? 1u : 0u);
+              }
+              if constexpr (PAIR) {
+                umma_f8_pair(d_tmem, d_al, d_bh, idesc8, 1u);
+                umma_f8_pair(d_tmem, d_ah, d_bl, idesc8, 1u);
+              } else {
+                umma_f8(d_tmem, d_al, d_bh, idesc8, 1u);
+                umma_f8(d_tmem, d_ah, d_bl, idesc8, 1u);
+              }
+            }
           }
           else
 #endif
@@ -262,12 +293,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               umma_f16_pair(d_tmem, a_lo, b_hi, idesc, first);
               umma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1u);
               umma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1u);
-#ifdef DD_PROBES
-            } else if (p.fp8_probe == 4) {  // ordering probe: the previous order
-              umma_f16(d_tmem, a_lo, b_hi, idesc, first);
-              umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
-#endif
             } else {
               umma_f16(d_tmem, a_lo, b_hi, idesc, first);
               umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);

@@ -86,8 +86,10 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: whole warp walks the loop, one
+    // elected lane issues the three copies of a stage back to back (see conv_halo.cuh)
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -98,10 +100,13 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
         for (int kc = 0; kc < C::KC; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = stage_ptr(stage);
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_3d(s, &tmW, &full_bar[stage], kc * BK, 0, tap);
-          tma_load_4d(s + C::W_BYTES, &tmP_hi, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
-          tma_load_4d(s + C::W_BYTES + C::P_BYTES, &tmP_lo, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+          if (leader) {
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_3d(s, &tmW, &full_bar[stage], kc * BK, 0, tap);
+            tma_load_4d(s + C::W_BYTES, &tmP_hi, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+            tma_load_4d(s + C::W_BYTES + C::P_BYTES, &tmP_lo, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+          }
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;

@@ -12,7 +12,7 @@
 // swizzled layout tcgen05 reads, and TMA's out-of-bounds zero fill *is* the conv's zero padding.
 // Weights are pre-packed [tap][COUT][CIN] fp16 hi/lo and fetched by a 3-D map with box {BK, COUT, 1}.
 //
-// Roles (256 threads, persistent over tiles): warp0.lane0 = TMA producer, warp1.lane0 = MMA issuer,
+// Roles (256 threads, persistent over tiles): warp 0 / 3 = TMA producers, warp 1 = MMA issuer (one elected lane each),
 // warp2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> regs -> +bias -> HBM, GroupNorm partial sums
 // by warp shuffle).  Two TMEM accumulators so tile i's epilogue overlaps tile i+1's MMAs.
 //
@@ -131,11 +131,12 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
   auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
 
-  if ((warp == 0 || warp == 3) && lane == 0) {
+  if (warp == 0 || warp == 3) {
     // ------------------------------------------------------------------ TMA producers: warp 0 feeds the activation
-    // planes, warp 3 the weight planes (a single thread issuing all four bulk-tensor copies per stage was the
-    // pipeline's bottleneck: ~160 ns per issued copy)
+    // planes, warp 3 the weight planes.  The whole warp walks the loop and one elected lane issues the copies (a lone
+    // `lane == 0` thread got every cp.async.bulk.tensor wrapped in an ELECT / BRA.U.ANY loop; see conv_halo.cuh)
     const bool act = (warp == 0);
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -148,15 +149,18 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int kc = 0; kc < C::KC; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = stage_ptr(stage);
-          if (act) {
-            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
-            tma_load_4d(s, &tmA_hi, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
-            tma_load_4d(s + C::A_BYTES, &tmA_lo, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_BYTES);
-            tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * BK, 0, tap);
-            tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * BK, 0, tap);
+          if (leader) {
+            if (act) {
+              mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
+              tma_load_4d(s, &tmA_hi, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+              tma_load_4d(s + C::A_BYTES, &tmA_lo, &full_bar[stage], kc * BK, x0 + dx, y0 + dy, img);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_BYTES);
+              tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * BK, 0, tap);
+              tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * BK, 0, tap);
+            }
           }
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -243,6 +247,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
       float tsum[4] = {0.f, 0.f, 0.f, 0.f}, tsq[4] = {0.f, 0.f, 0.f, 0.f};
       bool overflow = false;
+#ifdef DD_PROBES
       if (p.fp8_probe == 2) {  // timing probe (DD_FP8_PROBE=2): no epilogue work at all -> the mainloop's own tile rate
         tc_fence_before();
         __syncwarp();
@@ -250,6 +255,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         buf ^= 1;
         continue;
       }
+#endif
 #pragma unroll
       for (int cj = 0; cj < NCH / C::EPI_SETS; ++cj) {
         const int ch0 = (cj * C::EPI_SETS + es) * C::CH;  // compile-time when there is one set (es == 0)

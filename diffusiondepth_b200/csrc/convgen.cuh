@@ -98,10 +98,11 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
 
-  if ((warp == 0 || warp == 3) && lane == 0) {
-    // two TMA producers: warp 0 issues the activation copies, warp 3 the weight copies.  Each cp.async.bulk.tensor costs
-    // its issuing thread ~160 ns; four per 32-channel stage from one thread (0.64 us) were slower than the stage's MMAs
+  if (warp == 0 || warp == 3) {
+    // two TMA producers: warp 0 issues the activation copies, warp 3 the weight copies; the whole warp walks the loop,
+    // one elected lane issues (consecutive UTMALDGs instead of an ELECT / branch loop per copy; see conv_halo.cuh)
     const bool act = (warp == 0);
+    const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
@@ -114,19 +115,22 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = stage_ptr(stage);
           const int ax = x0 * p.stride + dx, ay = y0 * p.stride + dy;
-          if (!act) {
-            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_BYTES);
-            tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * C::BK, nt * NT, tap);
-            tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * C::BK, nt * NT, tap);
-          } else if (kc < p.kc0) {
-            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
-            tma_load_4d(s, &tmA0_hi, &full_bar[stage], kc * C::BK, ax, ay, img);
-            tma_load_4d(s + C::A_BYTES, &tmA0_lo, &full_bar[stage], kc * C::BK, ax, ay, img);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
-            tma_load_4d(s, &tmA1_hi, &full_bar[stage], (kc - p.kc0) * C::BK, ax, ay, img);
-            tma_load_4d(s + C::A_BYTES, &tmA1_lo, &full_bar[stage], (kc - p.kc0) * C::BK, ax, ay, img);
+          if (leader) {
+            if (!act) {
+              mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_BYTES);
+              tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * C::BK, nt * NT, tap);
+              tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * C::BK, nt * NT, tap);
+            } else if (kc < p.kc0) {
+              mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
+              tma_load_4d(s, &tmA0_hi, &full_bar[stage], kc * C::BK, ax, ay, img);
+              tma_load_4d(s + C::A_BYTES, &tmA0_lo, &full_bar[stage], kc * C::BK, ax, ay, img);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
+              tma_load_4d(s, &tmA1_hi, &full_bar[stage], (kc - p.kc0) * C::BK, ax, ay, img);
+              tma_load_4d(s + C::A_BYTES, &tmA1_lo, &full_bar[stage], (kc - p.kc0) * C::BK, ax, ay, img);
+            }
           }
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;

@@ -387,6 +387,10 @@ struct dd_engine {
   dd_config cfg;
   int sm_count = 0;
   unsigned long long* clk_probe = nullptr;  // DD_CLK_PROBE=1: per-launch SM cycles / nanoseconds (dd_bench_conv)
+  // tuning / timing probes: read from the environment ONCE in dd_create, and only in a -DDD_PROBES build
+  // (profiles/README.md); a product build ignores the variables altogether
+  int probe_fp8 = 0, swap_mask = -1, halo_mask = -1, pair_mask = -1;
+  bool want_clk_probe = false;
   bool weights_ready = false;
   std::map<std::string, Raw> raw;
   // packed parameters (device memory owned by the engine)
@@ -558,7 +562,7 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
   a.out_lo = out_lo;
   a.split_scale = kActScale;
   a.status = e->status;
-  a.fp8_probe = getenv("DD_FP8_PROBE") ? atoi(getenv("DD_FP8_PROBE")) : 0;
+  a.fp8_probe = e->probe_fp8;
   a.clk_probe = e->clk_probe;
   cudaError_t err = cudaSuccess;
   e->launches++;
@@ -566,12 +570,10 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
   for (int i = 0; i < 4; ++i)
     if (stats_partial == e->stats[i]) which = i;
   if (which >= 0) e->stats_tiles_img[which] = g.tiles_img;
-  bool swap_here = kUseSwap[L.sid];
-  if (const char* m = getenv("DD_SWAP_MASK")) swap_here = (atoi(m) >> L.sid) & 1;  // tuning probe (profiles/swap_probe.py)
+  const bool swap_here = e->swap_mask >= 0 ? ((e->swap_mask >> L.sid) & 1) : kUseSwap[L.sid];
   const bool use_swap = (e->cfg.flags & DD_FLAG_SWAP_NARROW) && !(e->cfg.flags & DD_FLAG_SIMT_CONV) &&
                         swap_here && kSwapBK[L.sid] > 0 && epi != dd::EPI_SPLIT;
-  bool halo_here = kUseHalo[L.sid];
-  if (const char* m = getenv("DD_HALO_MASK")) halo_here = (atoi(m) >> L.sid) & 1;  // tuning probe
+  const bool halo_here = e->halo_mask >= 0 ? ((e->halo_mask >> L.sid) & 1) : kUseHalo[L.sid];
   const bool use_halo = (e->cfg.flags & DD_FLAG_HALO_CONV) && !(e->cfg.flags & DD_FLAG_SIMT_CONV) && halo_here;
   if (!use_swap) {  // tile geometry of the kernel actually launched
     const int tw = use_halo ? dd::HALO_TW : dd::TILE_W, th = use_halo ? dd::HALO_TH : dd::TILE_H;
@@ -626,7 +628,8 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
     const int hbk = kHaloBK[L.sid];
     if ((rc = make_strip_map(&ma_hi, in_hi, g.B, g.h, g.w, s.cin, hbk))) return rc;
     if ((rc = make_strip_map(&ma_lo, in_lo, g.B, g.h, g.w, s.cin, hbk))) return rc;
-    const bool use_pair = (e->cfg.flags & DD_FLAG_PAIR_WIDE) && kUsePair[L.sid];
+    const bool use_pair = (e->cfg.flags & DD_FLAG_PAIR_WIDE) &&
+                          (e->pair_mask >= 0 ? ((e->pair_mask >> L.sid) & 1) && s.cout == 256 : kUsePair[L.sid]);
     if (use_pair) {
 #define PAIR_CASE(ID, CI, CO, BK)                                                                                   \
   case ID:                                                                                                          \
@@ -1407,6 +1410,13 @@ int dd_create(const dd_config* cfg, dd_handle* out) {
   dd_engine* e = new dd_engine();
   e->cfg = *cfg;
   e->sm_count = prop.multiProcessorCount;
+#ifdef DD_PROBES
+  if (const char* v = getenv("DD_FP8_PROBE")) e->probe_fp8 = atoi(v);
+  if (const char* v = getenv("DD_SWAP_MASK")) e->swap_mask = atoi(v);
+  if (const char* v = getenv("DD_HALO_MASK")) e->halo_mask = atoi(v);
+  if (const char* v = getenv("DD_PAIR_MASK")) e->pair_mask = atoi(v);
+  e->want_clk_probe = getenv("DD_CLK_PROBE") != nullptr;
+#endif
   if (cudaMallocHost(&e->status_host, 64) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
       configure_all_kernels() != cudaSuccess || configure_halo_kernels() != cudaSuccess ||
@@ -1578,6 +1588,9 @@ int dd_finalize_weights(dd_handle h, void* cuda_stream) {
   h->rn.ready = false;
   if (h->rn.enabled)
     if ((rc = pack_resnet(h, st, scratch))) return rc;
+  // the registered pointers were borrowed for this call only (include/dd_engine.h): forget them, so a later finalize
+  // cannot read memory the caller has freed in the meantime — every key has to be registered again
+  h->raw.clear();
   h->weights_ready = true;
   return DD_OK;
 }
@@ -2140,7 +2153,7 @@ int dd_bench_conv(dd_handle h, int32_t cin, int32_t cout, int32_t iters, float* 
     if ((rc = run_conv(h, layer, in_hi, in_lo, kActScale, split_out ? dd::EPI_SPLIT : dd::EPI_F32_STATS, h->Y,
                        h->stats[0], h->S_hi[0], h->S_lo[0], st)))
       return rc;
-  if (getenv("DD_CLK_PROBE") && !h->clk_probe) CUDA_TRY(cudaMalloc(&h->clk_probe, 16));
+  if (h->want_clk_probe && !h->clk_probe) CUDA_TRY(cudaMalloc(&h->clk_probe, 16));
   if (h->clk_probe) CUDA_TRY(cudaMemsetAsync(h->clk_probe, 0, 16, st));
   CUDA_TRY(cudaEventRecord(e0, st));
   for (int i = 0; i < iters; ++i)
