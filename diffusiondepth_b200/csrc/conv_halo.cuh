@@ -25,8 +25,18 @@ constexpr int HALO_TW = 8;
 // halves, so per SM the weight tile is written to and read from shared memory half as often.  Measured motivation
 // (profiles/README.md): the single-CTA kernel moves ~110 KB through each SM's shared-memory port per (chunk, tap) stage
 // = ~860 cycles at 128 B/clk, above the 768 cycles of tensor work -> it is shared-memory-port bound.
-template <int CIN, int COUT, int BK, bool PAIR = false>
+// F8 = true (PAIR only): FP8 CORRECTION PRODUCTS.  The operand planes are hi = fp16(s x), a8 = e4m3(s x / 4) and
+// l8 = e4m3((s x - hi) * 512) (weights: hi = fp16(t w), w8 = e4m3(t w / 512), lw8 = e4m3((t w - hi) * 4)), and a
+// 32-channel chunk issues  D += l8 * w8 ; D += a8 * lw8  (kind::f8f6f4, K = 32 each; the power-of-two scales cancel:
+// 512 / 512 = 1, 4 / 4 = 1)  then  D += hi * hi  (kind::f16, 2 x K = 16)  into the ONE fp32 accumulator: 4 MMAs of 2
+// pass-equivalents instead of 6 MMAs of 3.  Measured (profiles/README.md round 2): on CTA pairs a K = 32 e4m3 MMA
+// costs ~175 cycles against 2 x 128 for the same K in fp16 (single CTA: 260 — it needs cta_group::2), and under the
+// 1 kW power cap the clock rises with the lighter MMA mix: 256->256 at C3 629 us vs 948 us (3 fp16 passes on pairs)
+// vs 1119 us (round 1).  Parity cost (oracle/probe_fp8_static.py, real C3 case vs the reference golden): max |dz|
+// 3.4e-4 / rms 7e-5 instead of 2.3e-5 / 4.5e-6, tolerance 1e-3.  Same bytes per element in HBM (2 + 1 + 1).
+template <int CIN, int COUT, int BK, bool PAIR = false, bool F8 = false>
 struct HaloCfg {
+  static_assert(!F8 || (PAIR && BK == 32 && COUT == 256), "fp8 corrections: pair kernel, 32-channel chunks, wide layers");
   static_assert((CIN % BK == 0 || CIN < BK) && CIN % 16 == 0 && (BK == 16 || BK == 32), "bad K chunk");
   // CIN < BK (16-channel latent, BK = 32) is supported — the box is wider than the channel extent, TMA zero-fills the
   // rest and only CIN / 16 K-steps are issued — but measured slower on 16->64 (110 vs 82 us), so the engine keeps BK = 16.
@@ -36,11 +46,16 @@ struct HaloCfg {
   static constexpr int STRIP_ROWS = (HALO_TH + 2) * HALO_TW;        // 144 pixel rows
   static constexpr int STRIP_BYTES = STRIP_ROWS * ROW_BYTES;        // one plane, one dx
   static constexpr int STRIP_PAD = (STRIP_BYTES + 1023) / 1024 * 1024;
-  static constexpr int A_SLOT = 6 * STRIP_PAD;                      // 3 dx x (hi, lo)
+  static constexpr int STRIP8_BYTES = STRIP_ROWS * BK;              // e4m3 plane: one byte per channel
+  static constexpr int STRIP8_PAD = (STRIP8_BYTES + 1023) / 1024 * 1024;
+  static constexpr int DX_STRIDE = F8 ? STRIP_PAD + 2 * STRIP8_PAD : 2 * STRIP_PAD;  // planes of one dx: hi, lo | hi, a8, l8
+  static constexpr int A_SLOT = 3 * DX_STRIDE;
   static constexpr int B_ROWS = PAIR ? COUT / 2 : COUT;             // weight rows this CTA stages
   static constexpr int B_TILE = B_ROWS * ROW_BYTES;                 // one plane, one tap, one chunk
   static constexpr int B_TILE_PAD = (B_TILE + 1023) / 1024 * 1024;
-  static constexpr int B_SLOT = 2 * B_TILE_PAD;
+  static constexpr int B8_TILE = B_ROWS * BK;
+  static constexpr int B8_TILE_PAD = (B8_TILE + 1023) / 1024 * 1024;
+  static constexpr int B_SLOT = F8 ? B_TILE_PAD + 2 * B8_TILE_PAD : 2 * B_TILE_PAD;
   static constexpr int A_SLOTS = 2;
   // Two sets of four epilogue warps where the epilogue is on the critical path: Cout = 64 (two chunks, one per set; each
   // set then owns two GroupNorm groups) and the pair kernel's 64->256 layer (K = 576: 18 stages per tile, so draining a
@@ -60,8 +75,8 @@ struct HaloCfg {
   static constexpr int B_SLOTS = B_RESIDENT ? 9 * KC : (B_SLOTS_RAW > 8 ? 8 : B_SLOTS_RAW);
   static_assert(B_SLOTS >= 2, "B ring too small");
   static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 1024 + XPOSE_BYTES;
-  static constexpr int A_TX = 6 * STRIP_BYTES;
-  static constexpr int B_TX = 2 * B_TILE;
+  static constexpr int A_TX = F8 ? 3 * (STRIP_BYTES + 2 * STRIP8_BYTES) : 6 * STRIP_BYTES;
+  static constexpr int B_TX = F8 ? B_TILE + 2 * B8_TILE : 2 * B_TILE;
   // Narrow-N layers: back-to-back MMAs into ONE accumulator serialise on its read-modify-write latency (~105 cycles
   // per MMA measured for N = 64 / 16, vs 32-48 cycles of work).  Give each of the three split passes its own TMEM
   // accumulator (three independent chains, summed in the epilogue; the small terms also add up separately).
@@ -73,12 +88,15 @@ struct HaloCfg {
   static constexpr int GROUP_CH = COUT / 4;
 };
 
-template <int CIN, int COUT, int BK, int EPI, bool PAIR = false>
-__global__ void __launch_bounds__((HaloCfg<CIN, COUT, BK, PAIR>::THREADS), 1)
+// F8: tmA_lo / tmB_lo are the maps of the activation a8 / the weight w8 planes, tmA_x / tmB_x those of l8 / lw8 (uint8 maps,
+// 32-byte swizzle); without F8 the two extra maps are unused copies.
+template <int CIN, int COUT, int BK, int EPI, bool PAIR = false, bool F8 = false>
+__global__ void __launch_bounds__((HaloCfg<CIN, COUT, BK, PAIR, F8>::THREADS), 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const __grid_constant__ CUtensorMap tmA_x, const __grid_constant__ CUtensorMap tmB_x,
                     const ConvArgs p) {
-  using C = HaloCfg<CIN, COUT, BK, PAIR>;
+  using C = HaloCfg<CIN, COUT, BK, PAIR, F8>;
   static_assert(!PAIR || C::NACC == 1, "pair mode is for the wide layers");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -107,6 +125,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     tma_prefetch_desc(&tmA_lo);
     tma_prefetch_desc(&tmB_hi);
     tma_prefetch_desc(&tmB_lo);
+    if constexpr (F8) {
+      tma_prefetch_desc(&tmA_x);
+      tma_prefetch_desc(&tmB_x);
+    }
     // pair mode: the leader's full barriers take one arrive.expect_tx from each CTA's producer; its tempty barriers take
     // the four epilogue warps of both CTAs; empty / tfull barriers live in each CTA and are hit by multicast commits
     for (int s = 0; s < C::A_SLOTS; ++s) {
@@ -157,8 +179,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             mbar_arrive_expect_tx_cluster(lead, C::A_TX);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-              tma_load_4d_pair(s + (2 * dx) * C::STRIP_PAD, &tmA_hi, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
-              tma_load_4d_pair(s + (2 * dx + 1) * C::STRIP_PAD, &tmA_lo, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+              uint8_t* d = s + dx * C::DX_STRIDE;
+              tma_load_4d_pair(d, &tmA_hi, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+              tma_load_4d_pair(d + C::STRIP_PAD, &tmA_lo, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+              if constexpr (F8)
+                tma_load_4d_pair(d + C::STRIP_PAD + C::STRIP8_PAD, &tmA_x, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
             }
           } else {
             mbar_arrive_expect_tx(&a_full[sa], C::A_TX);
@@ -193,6 +218,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               mbar_arrive_expect_tx_cluster(lead, C::B_TX);
               tma_load_3d_pair(s, &tmB_hi, lead, kc * BK, static_cast<int>(rank) * C::B_ROWS, tap);
               tma_load_3d_pair(s + C::B_TILE_PAD, &tmB_lo, lead, kc * BK, static_cast<int>(rank) * C::B_ROWS, tap);
+              if constexpr (F8)
+                tma_load_3d_pair(s + C::B_TILE_PAD + C::B8_TILE_PAD, &tmB_x, lead, kc * BK, static_cast<int>(rank) * C::B_ROWS, tap);
             } else {
               mbar_arrive_expect_tx(&b_full[sb], C::B_TX);
               tma_load_3d(s, &tmB_hi, &b_full[sb], kc * BK, 0, tap);
@@ -229,11 +256,25 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           mbar_wait(&b_full[sb], C::B_RESIDENT ? 0u : pb);  // resident: phase 0 completes once and stays complete
           tc_fence_after();
           // strip dx, dy rows down: 8-pixel groups stay dense (8 * ROW_BYTES) and aligned to the swizzle repeat
-          const uint32_t sa_hi = a_base + (2 * dx) * C::STRIP_PAD + dy * HALO_TW * C::ROW_BYTES;
-          const uint32_t sa_lo = sa_hi + C::STRIP_PAD;
+          const uint32_t sa_hi = a_base + dx * C::DX_STRIDE + dy * HALO_TW * C::ROW_BYTES;
+          const uint32_t sa_lo = a_base + dx * C::DX_STRIDE + C::STRIP_PAD + dy * HALO_TW * (F8 ? BK : C::ROW_BYTES);
           const uint32_t sb_hi = smem_u32(b_ring + sb * C::B_SLOT);
           const uint32_t sb_lo = sb_hi + C::B_TILE_PAD;
           if (leader) {
+          if constexpr (F8) {
+            // e4m3 planes: 32-byte rows (one K = 32 instruction per plane pair), 8-row groups of 256 B = the 32-byte
+            // swizzle repeat, so the dy row advance (8 pixels x 32 B) keeps the canonical K-major layout as well
+            constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) |
+                                        (static_cast<uint32_t>((2 * TILE_M) >> 4) << 24);  // D f32, A / B e4m3
+            const uint32_t sa_l8 = sa_lo + C::STRIP8_PAD;   // sa_lo = a8
+            const uint32_t sb_lw8 = sb_lo + C::B8_TILE_PAD;  // sb_lo = w8
+            umma_f8_pair(d_tmem, umma_smem_desc(sa_l8, BK), umma_smem_desc(sb_lo, BK), idesc8, (kc | tap) != 0 ? 1u : 0u);
+            umma_f8_pair(d_tmem, umma_smem_desc(sa_lo, BK), umma_smem_desc(sb_lw8, BK), idesc8, 1u);
+#pragma unroll
+            for (int k = 0; k < C::KSTEPS; ++k)
+              umma_f16_pair(d_tmem, umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES), umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES),
+                            idesc, 1u);
+          } else {
 #ifdef DD_PROBES  // timing probes of DESIGN.md §8 / profiles/README.md (build with -DDD_PROBES); results are garbage
           if (p.fp8_probe == 3 || p.fp8_probe == 1) {
             // 3: the intrinsic rate of kind::f8f6f4 — three K = 32 e4m3 MMAs per (chunk, tap) stage and nothing else;
@@ -299,6 +340,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
             }
           }
+          }  // !F8
           if constexpr (PAIR) umma_commit_pair(&b_empty[sb], 3);
           else if constexpr (!C::B_RESIDENT) umma_commit(&b_empty[sb]);
           }  // leader
@@ -413,6 +455,32 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 #pragma unroll
             for (int j = 0; j < C::CH / 4; ++j)
               dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else if (p.out_a8 != nullptr) {
+            // planes for a consumer with fp8 corrections: hi (fp16) + a8 + l8 (e4m3), 64 + 32 + 32 bytes per 32 channels
+            if constexpr (C::CH == 32) {
+              __align__(16) __half hi[32];
+              __align__(16) uint16_t a8[16];
+              __align__(16) uint16_t l8[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float s0 = v[j] * p.split_scale, s1 = v[j + 1] * p.split_scale;
+                overflow |= (fabsf(s0) > kF8ActMax) | (fabsf(s1) > kF8ActMax);
+                hi[j] = __float2half_rn(s0);
+                hi[j + 1] = __float2half_rn(s1);
+                a8[j >> 1] = e4m3x2(s0 * kF8ActDiv, s1 * kF8ActDiv);
+                l8[j >> 1] = e4m3x2((s0 - __half2float(hi[j])) * kF8LoMul, (s1 - __half2float(hi[j + 1])) * kF8LoMul);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(p.out_hi + pix * COUT + ch0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dh[j] = reinterpret_cast<const uint4*>(hi)[j];
+              uint4* da = reinterpret_cast<uint4*>(p.out_a8 + pix * COUT + ch0);
+              uint4* dl = reinterpret_cast<uint4*>(p.out_l8 + pix * COUT + ch0);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                da[j] = reinterpret_cast<const uint4*>(a8)[j];
+                dl[j] = reinterpret_cast<const uint4*>(l8)[j];
+              }
+            }
           } else {
             __align__(16) __half hi[C::CH];
             __align__(16) __half lo[C::CH];

@@ -70,7 +70,49 @@ __global__ void split_planes_kernel(const float* __restrict__ x, __half* __restr
   if (ov) atomicOr(status, 1);
 }
 
+// fp32 NHWC -> fp16 hi plane + e4m3 a8 / l8 planes (standalone-layer path of the fp8-correction kernel)
+__global__ void split_planes8_kernel(const float* __restrict__ x, __half* __restrict__ hi, uint8_t* __restrict__ a8,
+                                     uint8_t* __restrict__ l8, size_t n8, float scale, int* status) {
+  bool ov = false;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 u0 = reinterpret_cast<const float4*>(x)[2 * i], u1 = reinterpret_cast<const float4*>(x)[2 * i + 1];
+    const float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    __align__(16) __half h[8];
+    __align__(8) uint16_t pa[4];
+    __align__(8) uint16_t pl[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float s0 = v[j] * scale, s1 = v[j + 1] * scale;
+      ov |= (fabsf(s0) > kF8ActMax) | (fabsf(s1) > kF8ActMax);
+      h[j] = __float2half_rn(s0);
+      h[j + 1] = __float2half_rn(s1);
+      pa[j >> 1] = e4m3x2(s0 * kF8ActDiv, s1 * kF8ActDiv);
+      pl[j >> 1] = e4m3x2((s0 - __half2float(h[j])) * kF8LoMul, (s1 - __half2float(h[j + 1])) * kF8LoMul);
+    }
+    reinterpret_cast<uint4*>(hi)[i] = *reinterpret_cast<const uint4*>(h);
+    reinterpret_cast<uint2*>(a8)[i] = *reinterpret_cast<const uint2*>(pa);
+    reinterpret_cast<uint2*>(l8)[i] = *reinterpret_cast<const uint2*>(pl);
+  }
+  if (ov) atomicOr(status, 1);
+}
+
 // ------------------------------------------------------------------ weight pre-pack
+// fp8-correction weight planes [tap][COUT][CIN] bytes: w8 = e4m3(t w / 512) (partner of the activation l8, scaled by
+// 512), lw8 = e4m3((t w - fp16(t w)) * 4) (partner of a8, scaled by 1/4); t = the layer's fp16 weight scale
+__global__ void pack_conv_weight8_kernel(const float* __restrict__ w, uint8_t* __restrict__ w8, uint8_t* __restrict__ lw8,
+                                         int cout, int cin, float scale) {
+  const int n = cout * cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9, ci = (i / 9) % cin, co = i / (9 * cin);
+    const float s = w[i] * scale;
+    const float h = __half2float(__float2half_rn(s));
+    const size_t o = (static_cast<size_t>(tap) * cout + co) * cin + ci;
+    w8[o] = static_cast<uint8_t>(e4m3x2(s * (1.f / kF8LoMul), 0.f) & 0xff);
+    lw8[o] = static_cast<uint8_t>(e4m3x2((s - h) * (1.f / kF8ActDiv), 0.f) & 0xff);
+  }
+}
+
 // w [COUT][CIN][3][3] fp32 -> hi/lo fp16 [tap][COUT][CIN] (scaled) and fp32 [tap][CIN][COUT] (SIMT path)
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo,
                                         float* __restrict__ w_simt, int cout, int cin, float scale) {
@@ -160,9 +202,39 @@ struct ApplyArgs {
   float ry, rx;            // (ch-1)/(H-1), (cw-1)/(W-1) in fp32 as ATen computes them
   __half* out_hi;
   __half* out_lo;
+  uint8_t* out_a8;         // non-null: the consumer uses fp8 corrections -> write e4m3 planes a8 / l8 instead of fp16 lo
+  uint8_t* out_l8;
   float scale;
   int* status;
 };
+
+// 8 consecutive channels of one pixel -> operand planes (fp16 hi + fp16 lo, or fp16 hi + e4m3 a8 + e4m3 l8)
+__device__ __forceinline__ void store_planes8(const float (&v)[8], float scale, __half* out_hi, __half* out_lo,
+                                              uint8_t* out_a8, uint8_t* out_l8, size_t off, bool& ov) {
+  __align__(16) __half h[8];
+  if (out_a8 != nullptr) {
+    __align__(8) uint16_t a8[4];
+    __align__(8) uint16_t l8[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float s0 = v[j] * scale, s1 = v[j + 1] * scale;
+      ov |= (fabsf(s0) > kF8ActMax) | (fabsf(s1) > kF8ActMax);
+      h[j] = __float2half_rn(s0);
+      h[j + 1] = __float2half_rn(s1);
+      a8[j >> 1] = e4m3x2(s0 * kF8ActDiv, s1 * kF8ActDiv);
+      l8[j >> 1] = e4m3x2((s0 - __half2float(h[j])) * kF8LoMul, (s1 - __half2float(h[j + 1])) * kF8LoMul);
+    }
+    *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint2*>(out_a8 + off) = *reinterpret_cast<const uint2*>(a8);
+    *reinterpret_cast<uint2*>(out_l8 + off) = *reinterpret_cast<const uint2*>(l8);
+  } else {
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_f16(v[j], scale, h[j], l[j], ov);
+    *reinterpret_cast<uint4*>(out_hi + off) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
+  }
+}
 
 template <int C, int COND>
 __global__ void __launch_bounds__(256) gn_apply_split_kernel(const ApplyArgs a) {
@@ -237,12 +309,7 @@ __global__ void __launch_bounds__(256) gn_apply_split_kernel(const ApplyArgs a) 
   }
 
   bool ov = false;
-  __align__(16) __half h[VEC];
-  __align__(16) __half l[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) split_f16(v[j], a.scale, h[j], l[j], ov);
-  *reinterpret_cast<uint4*>(a.out_hi + off) = *reinterpret_cast<const uint4*>(h);
-  *reinterpret_cast<uint4*>(a.out_lo + off) = *reinterpret_cast<const uint4*>(l);
+  store_planes8(v, a.scale, a.out_hi, a.out_lo, a.out_a8, a.out_l8, off, ov);
   if (ov) atomicOr(a.status, 1);
 }
 
@@ -335,18 +402,16 @@ __global__ void __launch_bounds__(256) gn_apply_up_split_kernel(const ApplyArgs 
       const int x1 = x0 + (x0 < a.cw - 1 ? 1 : 0);
       const float lx1 = fx - x0, lx0 = 1.f - lx1;
       const int i0 = (x0 - xs) * C + c0, i1 = (x1 - xs) * C + c0;
-      __align__(16) __half h[8];
-      __align__(16) __half l[8];
+      float o8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float gn = fmaxf(fmaf(v[j], sa[c0 + j], sb[c0 + j]), 0.f);
         // (cond + te) interpolated exactly as the reference does it: te enters every tap
         const float up = ly0 * (lx0 * (r0[i0 + j] + te[j]) + lx1 * (r0[i1 + j] + te[j])) +
                          ly1 * (lx0 * (r1[i0 + j] + te[j]) + lx1 * (r1[i1 + j] + te[j]));
-        split_f16(up + gn, a.scale, h[j], l[j], ov);
+        o8[j] = up + gn;
       }
-      *reinterpret_cast<uint4*>(a.out_hi + off) = *reinterpret_cast<const uint4*>(h);
-      *reinterpret_cast<uint4*>(a.out_lo + off) = *reinterpret_cast<const uint4*>(l);
+      store_planes8(o8, a.scale, a.out_hi, a.out_lo, a.out_a8, a.out_l8, off, ov);
     }
   }
   if (ov) atomicOr(a.status, 1);

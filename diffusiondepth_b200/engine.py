@@ -51,6 +51,20 @@ def ddim_coefficients(alphas_cumprod: torch.Tensor, num_inference_steps: int, nu
     return ts, cx, ce
 
 
+class WorkspacePool:
+    """One growing device buffer shared by several engines that never run concurrently (the engines of one head):
+    a ragged last batch or a second image size then costs packed weights only, not another workspace (1.3 GB at C3)."""
+
+    def __init__(self, device):
+        self.device, self.buf = torch.device(device), None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None  # release before growing
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
 class DenoiseEngine:
     """One engine per (device, geometry).  `variant`: 'swin' (cond at half the latent resolution, bilinear
     upsample + convA/convB) or 'res' (cond at latent resolution)."""
@@ -58,7 +72,8 @@ class DenoiseEngine:
     def __init__(self, variant: str, batch: int, latent_hw: Sequence[int], cond_hw: Sequence[int],
                  num_inference_steps: int, device: torch.device, cuda_graph: bool = True,
                  simt_conv: bool = False, check_range: bool = False, halo_conv: bool = True,
-                 swap_narrow: bool = True, pair_wide: bool = True):
+                 swap_narrow: bool = True, pair_wide: bool = True, step_decode: bool = False, workspace_pool=None,
+                 fp8_corr: bool = True):
         self.lib = _cabi.load_library()
         device = torch.device(device)
         if device.type != "cuda":
@@ -69,7 +84,10 @@ class DenoiseEngine:
         self.steps = int(num_inference_steps)
         flags = (_cabi.FLAG_CUDA_GRAPH if cuda_graph else 0) | (_cabi.FLAG_SIMT_CONV if simt_conv else 0) | \
                 (_cabi.FLAG_CHECK_RANGE if check_range else 0) | (_cabi.FLAG_HALO_CONV if halo_conv else 0) | \
-                (_cabi.FLAG_SWAP_NARROW if swap_narrow else 0) | (_cabi.FLAG_PAIR_WIDE if pair_wide else 0)
+                (_cabi.FLAG_SWAP_NARROW if swap_narrow else 0) | (_cabi.FLAG_PAIR_WIDE if pair_wide else 0) | \
+                (_cabi.FLAG_STEP_DECODE if step_decode else 0) | (_cabi.FLAG_FP8_CORR if fp8_corr else 0)
+        self.fp8_corr = bool(fp8_corr)
+        self.step_decode = bool(step_decode)
         cfg = _cabi.DDConfig(_cabi.ABI_VERSION, {"res": _cabi.VARIANT_RES, "swin": _cabi.VARIANT_SWIN}[variant],
                              self.batch, self.latent_hw[0], self.latent_hw[1], self.cond_hw[0], self.cond_hw[1],
                              self.steps, device.index if device.index is not None else torch.cuda.current_device(),
@@ -78,6 +96,7 @@ class DenoiseEngine:
         _cabi.check(self.lib.dd_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self._ws: Optional[torch.Tensor] = None
+        self._pool = workspace_pool  # optional WorkspacePool shared by the engines of one head (one buffer per device)
         self._keep = []  # fp32 contiguous copies handed to dd_set_weight must outlive finalize
         self.producers = None
         self.backbone = None
@@ -140,6 +159,8 @@ class DenoiseEngine:
 
     def _workspace(self) -> torch.Tensor:
         need = int(self.lib.dd_workspace_bytes(self._h))
+        if self._pool is not None:
+            return self._pool.get(need + 1024)
         if self._ws is None or self._ws.numel() < need + 1024:
             self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
         return self._ws
@@ -201,6 +222,26 @@ class DenoiseEngine:
             C.c_void_p(latent.data_ptr() if want_latent else 0), C.c_void_p(logits.data_ptr() if want_logits else 0),
             C.c_void_p(depth.data_ptr()), C.c_void_p(self._aligned(ws)), ws.numel() - 1024, C.c_void_p(self._stream())))
         return depth, latent, logits
+
+    def denoise_decode_steps(self, cond: Optional[torch.Tensor], noise: torch.Tensor, want_latent=False,
+                             want_logits=False):
+        """As `denoise_decode`, additionally decoding the latent after every step inside the captured graph (the *Vis
+        heads' `pred_inter`): returns (depth_steps [T,B,1,2h,2w], latent, logits of the final step)."""
+        if not self.step_decode:
+            raise EngineError("engine was created without step_decode=True")
+        B, (h, w) = self.batch, self.latent_hw
+        if cond is not None:
+            self._check_in(cond, (B, 256, *self.cond_hw))
+        self._check_in(noise, (B, 16, h, w))
+        steps = torch.empty(self.steps, B, 1, 2 * h, 2 * w, device=self.device, dtype=torch.float32)
+        latent = torch.empty(B, 16, h, w, device=self.device, dtype=torch.float32) if want_latent else None
+        logits = torch.empty(B, 1, 2 * h, 2 * w, device=self.device, dtype=torch.float32) if want_logits else None
+        ws = self._workspace()
+        _cabi.check(self.lib.dd_denoise_decode_steps(
+            self._h, C.c_void_p(cond.data_ptr() if cond is not None else 0), C.c_void_p(noise.data_ptr()),
+            C.c_void_p(latent.data_ptr() if want_latent else 0), C.c_void_p(logits.data_ptr() if want_logits else 0),
+            C.c_void_p(steps.data_ptr()), C.c_void_p(self._aligned(ws)), ws.numel() - 1024, C.c_void_p(self._stream())))
+        return steps, latent, logits
 
     def denoiser_forward(self, cond: torch.Tensor, noisy: torch.Tensor, t) -> torch.Tensor:
         """eps = ScheduledCNNRefine(noisy, t, cond); t: int or per-image sequence."""

@@ -46,8 +46,10 @@ class Diffusion_DCbase_Model(nn.Module):
         else:
             with torch.no_grad(), exact_fp32():
                 fp = self.depth_backbone(img)
+        # the backbone travels with the call: an nn.DataParallel replica / deep copy of this model then packs ITS weights
+        extra = {'backbone': self.depth_backbone} if hasattr(head, "can_run_backbone") else {}
         return self.depth_head(fp, depth_map, depth_mask, gt_depth_map=gt_depth_map, return_loss=return_loss,
-                               weight_map=weight_map, instance_masks=instance_masks, image=img, **kwargs)
+                               weight_map=weight_map, instance_masks=instance_masks, image=img, **extra, **kwargs)
 
     def forward(self, sample):
         extra = {'noise': sample['noise']} if 'noise' in sample else {}

@@ -2,9 +2,17 @@
 bridge to the CUDA engine.
 
 Reference call chain being replaced (src/model/head/ddim_depth_estimate_res_swin_addHAHI.py):
-  forward :87-185  ->  pipeline(...) :130-144  = CNNDDIMPipiline.__call__ :254-303 (T x {denoiser :361-382,
-  DDIMScheduler.step})  ->  depth_transform.inv_t :146.
-Here: FPN / neck stay torch ops (step-invariant, once per image); loop + decoder = one C-ABI call."""
+  forward :87-185  ->  encoder t() :102, hahineck :110, FPN :112-122, pipeline(...) :130-144 =
+  CNNDDIMPipiline.__call__ :254-303 (T x {denoiser :361-382, DDIMScheduler.step})  ->  depth_transform.inv_t :146.
+Here all of it — and the backbone in front of it — runs inside the CUDA engine (C ABI, include/dd_engine.h) whenever the
+engine instantiates the architecture; the torch modules below only hold the parameters under the reference's keys.
+The torch-op producer path (TF32 off) remains for architectures the engine does not instantiate.
+
+The engine bits are imported absolutely (`diffusiondepth_b200.*`), everything else relatively, so that this package
+works both as `diffusiondepth_b200.model` and as the reference's top-level `model` (symlink into
+`src/`, tested by tests/test_dropin.py)."""
+import collections
+import copy
 import weakref
 from typing import Dict, Optional, Tuple
 
@@ -12,14 +20,39 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..._cabi import EngineError
-from ...engine import DECODER_KEYS, DENOISER_KEYS, ENCODER_KEYS, FUSE_KEYS, DenoiseEngine
+from diffusiondepth_b200._cabi import EngineError
+from diffusiondepth_b200.engine import (DECODER_KEYS, DENOISER_KEYS, ENCODER_KEYS, FUSE_KEYS, DenoiseEngine,
+                                        WorkspacePool)
 from .._blocks import ConvModule, exact_fp32
 from ..diffusers.schedulers.scheduling_ddim import DDIMScheduler
 from ..ops import depth_transform as _codec  # noqa: F401  (registers the codec classes)
 from ..registry import DEPTH_TRANSFORM
 
 FPN_DIM = 256
+MAX_ENGINES = 4  # per head: least-recently-used engines beyond this are closed (packed weights + CUDA graphs freed)
+
+
+def collect_tensors(module: nn.Module, prefix: str = "") -> Dict[str, torch.Tensor]:
+    """`module.state_dict(keep_vars=True)` that also works on `nn.DataParallel` replicas, whose parameters are plain
+    tensor attributes listed in `_former_parameters` (torch/nn/parallel/replicate.py) and absent from `state_dict()`."""
+    out: Dict[str, torch.Tensor] = {}
+
+    def walk(m, pre):
+        for k, v in m._parameters.items():
+            if v is not None:
+                out[pre + k] = v
+        for k, v in getattr(m, "_former_parameters", {}).items():
+            if v is not None:
+                out.setdefault(pre + k, v)
+        for k, v in m._buffers.items():
+            if v is not None and k not in m._non_persistent_buffers_set:
+                out[pre + k] = v
+        for k, c in m._modules.items():
+            if c is not None:
+                walk(c, pre + k + ".")
+
+    walk(module, prefix)
+    return out
 
 
 def _gn_conv_stack(cin, mid, cout):
@@ -96,11 +129,47 @@ class DDIMHeadBase(nn.Module):
         self.capture_logits = False      # tests: also keep the decoder's pre-sigmoid z of the last forward
         self.native_producers = True     # neck + FPN on the engine's tensor-core conv path when the pyramid allows
         self.native_backbone = True      # Swin-L backbone on the engine's GEMM/attention path (needs native_producers)
-        self.__dict__['_backbone_ref'] = None  # weakref to the model's depth_backbone (set by Diffusion_DCbase_Model)
+        self.fp8_corrections = True      # Swin heads: correction products of convA / convB as e4m3 MMAs (DD_FLAG_FP8_CORR;
+        #                                  ~1.5x on the dominant kernel, max |dz| 3.4e-4 of the 1e-3 budget on config 3).
+        #                                  False = the exact 3-pass fp16 split everywhere.
+        self.__dict__['_backbone_ref'] = None  # weakref to the model's depth_backbone (Diffusion_DCbase_Model passes the
+        #                                        backbone with every call; this is the fallback for direct head calls)
         self.capture_cond = False        # tests: keep the NCHW condition map of the last forward
         self.noise_generator: Optional[torch.Generator] = None
-        self._engines: Dict[Tuple, DenoiseEngine] = {}
-        self._packed_sig = {}
+        self._reset_engine_state()
+
+    def _reset_engine_state(self):
+        self.__dict__['_engines'] = collections.OrderedDict()  # key -> DenoiseEngine, least recently used first
+        self.__dict__['_packed'] = {}                          # key -> (tensor list, signature) of the packed weights
+        self.__dict__['_pools'] = {}                           # device -> WorkspacePool
+
+    def invalidate_engines(self):
+        """Close every engine (call after replacing Parameter OBJECTS; in-place updates, load_state_dict and .to() are
+        picked up automatically through data_ptr / _version)."""
+        for e in self._engines.values():
+            e.close()
+        self._reset_engine_state()
+
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(model) (EMA / eval copies): the copy gets its own engines, packed from ITS parameters, and its
+        denoiser operator bridges to the copy — never to the original's ctypes handles or weights."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_engines", "_packed", "_pools", "_backbone_ref"):
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new.__dict__['_backbone_ref'] = None
+        new._reset_engine_state()
+        new.model.__dict__['_bridge'] = weakref.ref(new)
+        return new
+
+    def _replicate_for_data_parallel(self):
+        """nn.DataParallel replicas (reference src/main.py:434): same idea — the replica bridges to itself and reads the
+        replica's (broadcast) tensors; engines are cached per device in the dict shared with the original."""
+        replica = super()._replicate_for_data_parallel()
+        replica.__dict__['_backbone_ref'] = None
+        return replica
 
     # ------------------------------------------------------------------------------------------ engine bridge
     def _engine_tensors(self):
@@ -113,9 +182,9 @@ class DDIMHeadBase(nn.Module):
 
     def _producer_tensors(self):
         sd = {}
-        for k, v in self.state_dict(keep_vars=True).items():
-            if k.startswith(("hahineck.", "conv_lateral.", "conv_up.")):
-                sd[k] = v
+        for name in ("hahineck", "conv_lateral", "conv_up"):
+            if name in self._modules:
+                sd.update(collect_tensors(self._modules[name], name + "."))
         return sd
 
     @staticmethod
@@ -131,8 +200,14 @@ class DDIMHeadBase(nn.Module):
     def attach_backbone(self, backbone):
         self.__dict__['_backbone_ref'] = weakref.ref(backbone)
 
-    def _backbone(self):
-        return self._backbone_ref() if self._backbone_ref is not None else None
+    def _backbone(self, given=None):
+        if given is not None:
+            return given
+        bb = self._backbone_ref() if self._backbone_ref is not None else None
+        if bb is None:
+            raise EngineError("native backbone requested but no backbone module is attached to this head "
+                              "(Diffusion_DCbase_Model passes it; direct callers use head.attach_backbone)")
+        return bb
 
     @staticmethod
     def swin_pyramid(image_hw):
@@ -175,46 +250,86 @@ class DDIMHeadBase(nn.Module):
                 return False
         return self._sizes_ok(self.backbone_pyramid(img.shape[-2:]))
 
-    def _engine(self, batch, latent_hw, cond_hw, device, feats=None, image_hw=None) -> DenoiseEngine:
-        """feats: backbone feature maps, or a (channels, sizes) pyramid spec -> native neck/FPN;
-        image_hw: additionally run the Swin backbone natively."""
-        native = feats is not None
-        if native and not isinstance(feats, tuple):
-            feats = ([f.shape[1] for f in feats], [tuple(f.shape[-2:]) for f in feats])
-        key = (batch, tuple(latent_hw), tuple(cond_hw), str(device), self.diffusion_inference_steps,
-               self.use_cuda_graph, native, tuple(image_hw) if image_hw is not None else None)
-        eng = self._engines.get(key)
+    def _gather(self, native, image_hw, backbone):
         tensors = self._engine_tensors()
         if native:
             tensors.update(self._producer_tensors())
         if image_hw is not None:
-            for k, v in self._backbone().state_dict(keep_vars=True).items():
+            for k, v in collect_tensors(self._backbone(backbone), "backbone.").items():
                 if v.is_floating_point():
-                    tensors["backbone." + k] = v
-        sig = tuple((t.data_ptr(), t._version) for t in tensors.values())
+                    tensors[k] = v
+        return tensors
+
+    def _engine(self, batch, latent_hw, cond_hw, device, feats=None, image_hw=None, backbone=None) -> DenoiseEngine:
+        """feats: backbone feature maps, or a (channels, sizes) pyramid spec -> native neck/FPN;
+        image_hw: additionally run the backbone natively (`backbone`: the module holding its parameters)."""
+        native = feats is not None
+        if native and not isinstance(feats, tuple):
+            feats = ([f.shape[1] for f in feats], [tuple(f.shape[-2:]) for f in feats])
+        device = torch.device(device)
+        key = (batch, tuple(latent_hw), tuple(cond_hw), str(device), self.diffusion_inference_steps,
+               self.use_cuda_graph, native, tuple(image_hw) if image_hw is not None else None,
+               bool(self.return_intermediates), bool(self.fp8_corrections))
+        eng = self._engines.get(key)
         if eng is None:
+            pool = self._pools.setdefault(str(device), WorkspacePool(device))
             eng = DenoiseEngine(self.variant, batch, latent_hw, cond_hw, self.diffusion_inference_steps, device,
-                                cuda_graph=self.use_cuda_graph, check_range=False)
+                                cuda_graph=self.use_cuda_graph, check_range=False,
+                                step_decode=bool(self.return_intermediates), workspace_pool=pool,
+                                fp8_corr=bool(self.fp8_corrections))
             if native:
                 eng.enable_producers(feats[0], feats[1], has_neck=self.has_neck)
             if image_hw is not None:
                 if self.variant == "swin":
                     eng.enable_backbone(image_hw)
                 else:
-                    eng.enable_backbone(image_hw, depths=[len(st) for st in self._backbone().layers], kind="resnet")
+                    eng.enable_backbone(image_hw, depths=[len(st) for st in self._backbone(backbone).layers], kind="resnet")
             ts, cx, ce = self.scheduler.fused_coefficients(self.diffusion_inference_steps)
             eng.set_schedule(ts, cx, ce)
             self._engines[key] = eng
-            self._packed_sig.pop(key, None)
-        if self._packed_sig.get(key) != sig:  # first use, or parameters changed (load_state_dict, .to(), ...)
+            self._packed.pop(key, None)
+            while len(self._engines) > MAX_ENGINES:  # a ragged last batch / a new image size must not pile up engines
+                old_key, old = self._engines.popitem(last=False)
+                old.close()
+                self._packed.pop(old_key, None)
+        else:
+            self._engines.move_to_end(key)
+        # Re-pack when a parameter changed.  The ~500 tensors are walked once per pack; per forward only their
+        # (data_ptr, _version) pairs are compared (0.3 ms instead of 2.6 ms for a Swin-L model).
+        packed = self._packed.get(key)
+        if packed is not None and packed[2] is not (backbone if image_hw is not None else None):
+            packed = None  # a different backbone module (DataParallel replica): look its tensors up again
+        if packed is None:
+            tensors = self._gather(native, image_hw, backbone)
+            sig = None
+        else:
+            tensors = packed[0]
+            sig = tuple((t.data_ptr(), t._version) for t in tensors.values())
+        if packed is None or sig != packed[1]:
+            if packed is not None:  # something changed: the owning modules may hold new tensors
+                tensors = self._gather(native, image_hw, backbone)
             eng.load_weights(tensors)
-            self._packed_sig[key] = sig
+            self._packed[key] = (tensors, tuple((t.data_ptr(), t._version) for t in tensors.values()),
+                                 backbone if image_hw is not None else None)
         return eng
+
+    def _any_engine(self, batch, latent_hw, cond_hw, device):
+        """An engine of this geometry for the bare operators (denoiser / decode): reuse the forward's engine (same
+        packed denoiser + codec weights) instead of packing a second one."""
+        want = (batch, tuple(latent_hw), tuple(cond_hw), str(torch.device(device)))
+        for key in reversed(self._engines):
+            if key[:4] == want and key[4] == self.diffusion_inference_steps and self._packed.get(key) is not None:
+                tensors, sig, _ = self._packed[key]
+                if tuple((t.data_ptr(), t._version) for t in tensors.values()) == sig:
+                    self._engines.move_to_end(key)
+                    return self._engines[key]
+                break
+        return self._engine(batch, latent_hw, cond_hw, device)
 
     def denoiser(self, noisy, t, cond):
         """`self.model(noisy, t, cond, None, None, None)` of the reference, on the engine."""
         B = noisy.shape[0]
-        eng = self._engine(B, noisy.shape[-2:], cond.shape[-2:], noisy.device)
+        eng = self._any_engine(B, noisy.shape[-2:], cond.shape[-2:], noisy.device)
         tl = t.reshape(-1).tolist() if torch.is_tensor(t) else t
         return eng.denoiser_forward(cond.contiguous().float(), noisy.contiguous().float(), tl)
 
@@ -242,9 +357,9 @@ class DDIMHeadBase(nn.Module):
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, fp, depth_map, depth_mask, gt_depth_map=None, return_loss=False, noise=None, image=None,
-                **kwargs):
+                backbone=None, **kwargs):
         """fp: backbone feature maps — or None, meaning "run the backbone natively from `image`" (the model
-        wrapper does that when `can_run_backbone` holds)."""
+        wrapper does that when `can_run_backbone` holds, and passes `backbone` = the module holding its weights)."""
         with_backbone = fp is None
         if with_backbone:
             B, dev, dtype = image.shape[0], image.device, torch.float32
@@ -271,18 +386,25 @@ class DDIMHeadBase(nn.Module):
             want_cond = self.capture_cond or self.training or self.eval_ddim_loss
             if with_backbone:
                 eng = self._engine(B, latent_hw, sizes[0], dev, feats=(list(self.fpn_in_channels), sizes),
-                                   image_hw=tuple(image.shape[-2:]))
+                                   image_hw=tuple(image.shape[-2:]), backbone=backbone)
                 eng.run_backbone(image.contiguous().float())
                 cond = eng.build_condition(None, want_cond=want_cond)
             else:
                 eng = self._engine(B, latent_hw, tuple(fp[0].shape[-2:]), dev, feats=fp)
                 cond = eng.build_condition(fp, want_cond=want_cond)
             gt_map_t = eng.encode(gt_depth_map.contiguous().float())  # returned as pred_init / gt_map_t only
-            refined_depth, refined_depth_t, logits = eng.denoise_decode(None, x_T, want_latent=True,
-                                                                        want_logits=self.capture_logits)
+            loop_cond = None
         else:
             eng = self._engine(B, latent_hw, tuple(cond.shape[-2:]), dev)
-            refined_depth, refined_depth_t, logits = eng.denoise_decode(cond, x_T, want_latent=True,
+            loop_cond = cond
+        inter = None
+        if self.return_intermediates:  # *Vis heads: inv_t of every intermediate latent, decoded inside the graph
+            steps, refined_depth_t, logits = eng.denoise_decode_steps(loop_cond, x_T, want_latent=True,
+                                                                      want_logits=self.capture_logits)
+            inter = list(steps.unbind(0))
+            refined_depth = inter[-1]
+        else:
+            refined_depth, refined_depth_t, logits = eng.denoise_decode(loop_cond, x_T, want_latent=True,
                                                                         want_logits=self.capture_logits)
         self.last_latent, self.last_logits, self.last_cond = refined_depth_t, logits, cond
         if self.check_range:
@@ -290,7 +412,7 @@ class DDIMHeadBase(nn.Module):
         ddim_loss = self._ddim_loss(cond, refined_depth_t) if (self.eval_ddim_loss or self.training) \
             else refined_depth.new_zeros(())
         return {'pred': refined_depth, 'pred_init': gt_map_t, 'blur_depth_t': gt_map_t, 'ddim_loss': ddim_loss,
-                'gt_map_t': gt_map_t, 'pred_uncertainty': None, 'pred_inter': None, 'weight_map': None,
+                'gt_map_t': gt_map_t, 'pred_uncertainty': None, 'pred_inter': inter, 'weight_map': None,
                 'guidance': None, 'offset': None, 'aff': None, 'gamma': None, 'confidence': None}
 
     def _ddim_loss(self, cond, latent):
@@ -298,6 +420,6 @@ class DDIMHeadBase(nn.Module):
         noise = torch.randn(latent.shape).to(latent.device)
         t = torch.randint(0, self.scheduler.num_train_timesteps, (latent.shape[0],), device=latent.device).long()
         noisy = self.scheduler.add_noise(latent, noise, t)
-        return F.mse_loss(self.model(noisy, t, cond, None, None, None), noise)
+        return F.mse_loss(self.denoiser(noisy, t, cond), noise)  # == self.model(noisy, t, cond, None, None, None)
 
     ddim_loss = _ddim_loss

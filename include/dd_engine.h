@@ -68,7 +68,14 @@ enum dd_flags {
   DD_FLAG_CHECK_RANGE = 1 << 2,/* after the call, sync and report DD_ERR_RANGE if the split overflowed */
   DD_FLAG_HALO_CONV = 1 << 3,  /* loop convs on the row-halo-reuse kernel (16x8 tiles, 2.7x less activation traffic) */
   DD_FLAG_SWAP_NARROW = 1 << 4, /* Cout <= 64 convs on the swapped-operand kernel (weights as A, 256 pixels as N) */
-  DD_FLAG_PAIR_WIDE = 1 << 5    /* Cout = 256 convs on CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256) */
+  DD_FLAG_PAIR_WIDE = 1 << 5,   /* Cout = 256 convs on CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256) */
+  DD_FLAG_STEP_DECODE = 1 << 6, /* reserve workspace for dd_denoise_decode_steps (T decoded maps; the *Vis heads) */
+  DD_FLAG_FP8_CORR = 1 << 7     /* Swin variant, with HALO_CONV | PAIR_WIDE: the two 256->256 convs compute the correction
+                                   products of the split (x_lo * w_hi, x_hi * w_lo) as e4m3 MMAs (kind::f8f6f4, K = 32) and
+                                   only hi * hi in fp16: 2 pass-equivalents instead of 3, ~1.5x on the dominant kernel.
+                                   Error per product ~2^-15 instead of ~2^-22 (DESIGN.md "Numerics": max |dz| 3.4e-4 on
+                                   BASELINE config 3, tolerance 1e-3); activations must stay below 112 in magnitude
+                                   (DD_ERR_RANGE otherwise).  Off = the exact 3-pass fp16 split everywhere. */
 };
 
 typedef struct dd_config {
@@ -96,8 +103,9 @@ int dd_destroy(dd_handle h);
 
 /* Register one parameter/buffer by its reference state_dict key relative to `depth_head.`
  * (e.g. "model.noise_embedding.0.weight", "depth_transform.conv_inv_transform.1.running_var").
- * `dev_ptr` is a device fp32 pointer in the reference's own layout/shape; it is read during
- * dd_finalize_weights only.  Unknown keys are rejected (DD_ERR_INVALID). */
+ * `dev_ptr` is a device fp32 pointer in the reference's own layout/shape; it is read during the next
+ * dd_finalize_weights only, which then forgets every registered pointer (a re-pack registers all keys again).
+ * Unknown keys are rejected (DD_ERR_INVALID). */
 int dd_set_weight(dd_handle h, const char* name, const float* dev_ptr, const int64_t* shape, int32_t ndim);
 
 /* Pre-pack: fold eval-BatchNorm into the decoder, repack conv weights tap-major, split them into
@@ -164,6 +172,13 @@ size_t dd_workspace_bytes(dd_handle h);
 int dd_denoise_decode(dd_handle h, const float* cond, const float* noise, float* latent_out, float* logit_out,
                       float* depth_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* The *Vis heads' variant (reference src/model/head/ddim_depth_estimate_res_swin_addHAHI_vis.py:130-149, pipeline
+ * :289-304 `image_list`): same loop, and `inv_t` of the latent after EVERY step, all inside the captured graph.
+ * depth_steps_out [T][B,1,2h,2w] (slice T-1 is the final `pred`); latent_out / logit_out (nullable) refer to the
+ * final step.  Needs DD_FLAG_STEP_DECODE at dd_create. */
+int dd_denoise_decode_steps(dd_handle h, const float* cond, const float* noise, float* latent_out, float* logit_out,
+                            float* depth_steps_out, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
 /* eps = ScheduledCNNRefine(noisy, t, cond): noisy [B,16,h,w], t[b] int64 host array (one per image),
  * eps_out [B,16,h,w]. */
 int dd_denoiser_forward(dd_handle h, const float* cond, const float* noisy, const int64_t* t_host, float* eps_out,
@@ -182,7 +197,8 @@ int dd_encode(dd_handle h, const float* depth, int32_t height, int32_t width, fl
  * DD_FLAG_CHECK_RANGE is set. */
 int dd_poll_status(dd_handle h, void* cuda_stream);
 
-/* Number of kernel launches the last dd_denoise_decode enqueued (graph nodes count individually). */
+/* Number of kernel launches the last forward (dd_run_backbone .. dd_denoise_decode) enqueued; graph nodes count
+ * individually. */
 int64_t dd_last_launch_count(dd_handle h);
 
 /* Standalone layer entry used by the parity tests and the roofline bench: one 3x3/s1/p1 convolution

@@ -38,6 +38,42 @@ GOLDEN = {
 }
 
 
+# "trained-like" twins: same architectures, parameters perturbed by `trainedify` below, so that the regime released
+# checkpoints live in (non-zero Swin relative-position tables, non-trivial BatchNorm running statistics, non-unit
+# LayerNorm / GroupNorm affines) is pinned to the real reference too.  96x160 -> 24x40 tokens: padded (28x42) and
+# shifted windows; 70x106 -> odd 35x53 latent, resampling FPN.
+GOLDEN_TRAINED = {
+    "g_swinl_small_trained": ("swinl", 5, 1, 96, 160),
+    "g_res18_trained": ("res18", 5, 2, 70, 106),
+}
+SEED_TRAINED = 99
+
+
+def trainedify(model, seed=SEED_TRAINED):
+    """Deterministically move a freshly constructed model (reference or mirror: same module tree / key order) into a
+    trained-like regime, in place.  CPU generator, fixed module order -> identical tensors wherever it runs."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(t, std, mean=0.0):
+        t.copy_(torch.randn(t.shape, generator=g) * std + mean)
+
+    def ru(t, lo, hi):
+        t.copy_(torch.rand(t.shape, generator=g) * (hi - lo) + lo)
+
+    with torch.no_grad():
+        for name, mod in model.named_modules():
+            cls = type(mod).__name__
+            if cls == "BatchNorm2d":
+                rn(mod.running_mean, 0.2); ru(mod.running_var, 0.5, 1.5); ru(mod.weight, 0.5, 1.5); rn(mod.bias, 0.2)
+            elif cls in ("LayerNorm", "GroupNorm") and getattr(mod, "weight", None) is not None:
+                ru(mod.weight, 0.7, 1.3); rn(mod.bias, 0.1)
+            tab = getattr(mod, "relative_position_bias_table", None)
+            if tab is not None:
+                rn(tab, 0.5)
+    return model
+
+
 def make_args(family, steps):
     return Namespace(model_name="Diffusion_DCbase_", inference_steps=steps, num_train_timesteps=1000,
                      **FAMILIES[family])

@@ -21,17 +21,18 @@ from oracle import configs, ref_import, reference_runner, restate  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def build_mirror(family, steps):
+def build_mirror(family, steps, trained=False):
     from diffusiondepth_b200.model import get
     args = configs.make_args(family, steps)
     torch.manual_seed(configs.SEED_WEIGHTS)
-    return get(args)(args).eval()
+    m = get(args)(args).eval()
+    return configs.trainedify(m) if trained else m
 
 
 def weight_checksum(sd):
     """sum |w| in fp64 over the hot-path parameters + a few producer tensors."""
     keys = sorted(k for k in sd if k.startswith("depth_head.model.") or "conv_inv_transform" in k
-                  or k.startswith("depth_head.conv_lateral"))
+                  or k.startswith("depth_head.conv_lateral") or k.endswith("relative_position_bias_table"))
     return float(sum(sd[k].double().abs().sum() for k in keys if sd[k].is_floating_point()))
 
 
@@ -49,9 +50,10 @@ def subsample(name, t, H, W):
 
 
 def generate(case):
-    family, T, B, H, W = configs.GOLDEN[case]
+    trained = case in configs.GOLDEN_TRAINED
+    family, T, B, H, W = (configs.GOLDEN_TRAINED if trained else configs.GOLDEN)[case]
     t0 = time.time()
-    mirror = build_mirror(family, T)
+    mirror = build_mirror(family, T, trained)
     sd = {k: v.detach().clone() for k, v in mirror.state_dict().items()}
     ref = ref_import.build_reference_model(ref_import.make_args(
         configs.FAMILIES[family]["backbone_module"], configs.FAMILIES[family]["backbone_name"],
@@ -90,5 +92,5 @@ def generate(case):
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 8)
-    for c in (sys.argv[1:] or list(configs.GOLDEN)):
+    for c in (sys.argv[1:] or list(configs.GOLDEN) + list(configs.GOLDEN_TRAINED)):
         generate(c)

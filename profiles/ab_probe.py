@@ -21,7 +21,8 @@ head = HEADS.build(dict(type="DDIMDepthEstimate_Swin_ADDHAHI", in_channels=[64,1
                         num_train_timesteps=1000, depth_feature_dim=16, loss_cfgs=[], init_cfg=None)).eval().to(dev)
 g = torch.Generator().manual_seed(0)
 noise = torch.randn(4, 16, 176, 608, generator=g).to(dev); cond = torch.randn(4, 256, 88, 304, generator=g).abs().to(dev)
-e = dd.DenoiseEngine("swin", 4, (176, 608), (88, 304), 20, dev, cuda_graph=True)
+kw = dict(fp8_corr=os.environ.get("AB_FP8", "1") == "1") if "fp8_corr" in dd.DenoiseEngine.__init__.__code__.co_varnames else {}
+e = dd.DenoiseEngine("swin", 4, (176, 608), (88, 304), 20, dev, cuda_graph=True, **kw)
 e.load_weights(head._engine_tensors()); e.set_schedule(*head.scheduler.fused_coefficients(20))
 tag = os.environ["AB_TAG"]
 if os.environ.get("AB_LOOP") == "1":
@@ -43,14 +44,18 @@ for cin, cout in shapes:
 
 CONFIGS = [
     ("r1 lib (lone-lane TMA producers)", R1, dict(AB_LOOP="1", AB_ALL="1")),
-    ("r2 lib (whole-warp producers)", LIB, dict(AB_LOOP="1", AB_ALL="1")),
-    ("probes: 256->256 single, 64->256 pair", PROBES, dict(DD_CLK_PROBE="1")),
+    ("r2 lib (product build, default flags)", LIB, dict(AB_LOOP="1", AB_ALL="1")),
+    ("r2 lib, exact 3-pass split (fp8_corr off)", LIB, dict(AB_LOOP="1", AB_ALL="1", AB_FP8="0")),
+    ("probes: 256->256 single, 64->256 pair", PROBES, dict(DD_CLK_PROBE="1", DD_PAIR_MASK="2")),
     ("probes: pairs for both", PROBES, dict(DD_CLK_PROBE="1", DD_PAIR_MASK="6")),
     ("probes: single both, fp8 only (3 x K32 e4m3)", PROBES, dict(DD_CLK_PROBE="1", DD_PAIR_MASK="0", DD_FP8_PROBE="3")),
     ("probes: pair both, fp8 only (3 x K32 e4m3)", PROBES, dict(DD_CLK_PROBE="1", DD_PAIR_MASK="6", DD_FP8_PROBE="3")),
     ("probes: single both, 2 fp16 + 2 fp8", PROBES, dict(DD_CLK_PROBE="1", DD_PAIR_MASK="0", DD_FP8_PROBE="1")),
     ("probes: pair both, 2 fp16 + 2 fp8", PROBES, dict(DD_CLK_PROBE="1", DD_PAIR_MASK="6", DD_FP8_PROBE="1")),
 ]
+ONLY = os.environ.get("AB_ONLY")  # comma-separated indices into CONFIGS
+if ONLY:
+    CONFIGS = [CONFIGS[int(i)] for i in ONLY.split(",")]
 for tag, lib, env in CONFIGS:
     if not os.path.exists(lib):
         print(f"[{tag}] skipped: {lib} missing", flush=True)

@@ -28,3 +28,30 @@ def _built():
     """The in-tree CUDA library must exist for every test session (the driver runs build() first)."""
     import __graft_entry__ as g
     g.build()
+
+
+_PARITY = []
+
+
+@pytest.fixture
+def parity_log():
+    """Record the margin a parity test measured (max / RMS |dz| on the decoder logit == relative depth error); the
+    session writes them to gpurun_out/parity_margins.json (copied to profiles/PARITY_rNN.json per round)."""
+    def log(case, against, dz):
+        dz = dz.double().flatten()
+        _PARITY.append({"case": case, "against": against, "max_dz": float(dz.max()), "rms_dz": float(dz.pow(2).mean().sqrt()),
+                        "n": int(dz.numel()), "tolerance": 1e-3})
+    return log
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_margins.json"), "w") as f:
+            json.dump({"metric": "|dz| on the decoder's pre-sigmoid logit (== relative depth error)", "rows": _PARITY}, f, indent=1)
+    except OSError:
+        pass

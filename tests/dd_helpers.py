@@ -18,21 +18,27 @@ def load_golden(case):
     return dict(z=z, family=str(z["family"]), T=T, B=B, H=H, W=W)
 
 
-def build_mirror(family, steps):
-    """The product's plugin model under the golden weight seed (cached per family; steps is mutable)."""
+def build_mirror(family, steps, trained=False):
+    """The product's plugin model under the golden weight seed (cached per (family, trained); steps is mutable).
+    trained=True: the trained-like regime of oracle.configs.trainedify (the `*_trained` goldens)."""
     from diffusiondepth_b200.model import get
-    if family not in _MIRRORS:
+    if (family, trained) not in _MIRRORS:
         args = configs.make_args(family, steps)
         torch.manual_seed(configs.SEED_WEIGHTS)
-        _MIRRORS[family] = get(args)(args).eval()
-    m = _MIRRORS[family]
+        m = get(args)(args).eval()
+        _MIRRORS[(family, trained)] = configs.trainedify(m) if trained else m
+    m = _MIRRORS[(family, trained)]
     m.depth_head.diffusion_inference_steps = steps
     return m
 
 
+def is_trained_case(case):
+    return case in configs.GOLDEN_TRAINED
+
+
 def weight_checksum(sd):
     keys = sorted(k for k in sd if k.startswith("depth_head.model.") or "conv_inv_transform" in k
-                  or k.startswith("depth_head.conv_lateral"))
+                  or k.startswith("depth_head.conv_lateral") or k.endswith("relative_position_bias_table"))
     return float(sum(sd[k].double().abs().sum() for k in keys if sd[k].is_floating_point()))
 
 

@@ -34,15 +34,20 @@ def _head_sd(head):
 
 
 # ------------------------------------------------------------------------------------------------ single layers
-@pytest.mark.parametrize("path", ["classic", "halo", "pair", "swap", "simt"])
+@pytest.mark.parametrize("path", ["classic", "halo", "pair", "swap", "simt", "pair_f8"])
 @pytest.mark.parametrize("cin,cout", SHAPES)
 def test_conv3x3_all_hot_path_shapes(cin, cout, path):
     """3-pass fp16 split on tcgen05 — classic 8x16-tile kernel, row-halo-reuse kernel, its CTA-pair (cta_group::2,
     M = 256) variant for Cout = 256 (odd tile counts leave the second CTA of the last pair a zero-filled tile),
     swapped-operand kernel for the narrow layers — and the fp32 CUDA-core check path, vs an fp64 reference; ragged
     tiles, a single tile, sub-tile images."""
+    if path == "pair_f8" and (cin, cout) != (256, 256):
+        pytest.skip("fp8 correction products serve the 256 -> 256 layers")
+    # pair_f8: correction products as e4m3 MMAs (DD_FLAG_FP8_CORR): ~2^-15 per product instead of ~2^-22
+    tol = 3e-4 if path == "pair_f8" else 3e-5
     eng = dd.DenoiseEngine("swin", 1, (8, 16), (4, 8), 2, DEV, cuda_graph=False, simt_conv=path == "simt",
-                           halo_conv=path in ("halo", "pair"), swap_narrow=path == "swap", pair_wide=path == "pair")
+                           halo_conv=path in ("halo", "pair", "pair_f8"), swap_narrow=path == "swap",
+                           pair_wide=path in ("pair", "pair_f8"), fp8_corr=path == "pair_f8")
     for (B, H, W) in [(2, 24, 40), (1, 8, 16), (1, 13, 21), (1, 5, 9), (2, 57, 76)]:
         g = torch.Generator().manual_seed(cin * 1000 + cout + H)
         x = torch.randn(B, cin, H, W, generator=g).to(DEV) * 3
@@ -51,12 +56,14 @@ def test_conv3x3_all_hot_path_shapes(cin, cout, path):
         y = eng.conv3x3(x, w, b)
         ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1)
         err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
-        assert err < 3e-5, (cin, cout, B, H, W, err)
+        assert err < tol, (cin, cout, B, H, W, err)
+        if path == "pair_f8":
+            assert err > 1e-6, "the fp8 path was not taken"
     eng.close()
 
 
 def test_conv_linearity_and_zero():
-    eng = dd.DenoiseEngine("swin", 1, (8, 16), (4, 8), 2, DEV, cuda_graph=False)
+    eng = dd.DenoiseEngine("swin", 1, (8, 16), (4, 8), 2, DEV, cuda_graph=False, fp8_corr=False)
     g = torch.Generator().manual_seed(1)
     x1, x2 = (torch.randn(1, 256, 16, 32, generator=g).to(DEV) for _ in range(2))
     w = (torch.randn(256, 256, 3, 3, generator=g) * 0.02).to(DEV)
@@ -68,10 +75,13 @@ def test_conv_linearity_and_zero():
 
 
 # ------------------------------------------------------------------------------------------------ operators
-@pytest.mark.parametrize("variant,hw", [("res", (19, 27)), ("swin", (18, 26)), ("swin", (8, 16))])
-def test_denoiser_operator_vs_oracle(variant, hw):
-    """eps = ScheduledCNNRefine(noisy, t, cond) with per-image t — vs the fp64 restatement."""
+@pytest.mark.parametrize("variant,hw,fp8", [("res", (19, 27), False), ("swin", (18, 26), False), ("swin", (8, 16), False),
+                                            ("swin", (18, 26), True)])
+def test_denoiser_operator_vs_oracle(variant, hw, fp8):
+    """eps = ScheduledCNNRefine(noisy, t, cond) with per-image t — vs the fp64 restatement (exact 3-pass split, and the
+    fp8-correction mode of the two wide convs at its own error level)."""
     head = (_res_head if variant == "res" else _swin_head)(5).to(DEV)
+    head.fp8_corrections = fp8
     sd = _head_sd(head)
     B, (h, w) = 2, hw
     chw = (h, w) if variant == "res" else ((h + 1) // 2, (w + 1) // 2)
@@ -82,7 +92,7 @@ def test_denoiser_operator_vs_oracle(variant, hw):
     eps = head.model(noisy.to(DEV), t.to(DEV), cond.to(DEV), None, None, None)
     ref = restate.denoiser(sd, noisy.double(), t, cond.double(), variant)
     assert eps.shape == ref.shape and (eps >= 0).all()
-    assert (eps.double().cpu() - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+    assert (eps.double().cpu() - ref).abs().max().item() < (2e-3 if fp8 else 2e-4) * max(1.0, ref.abs().max().item())
 
 
 def test_decoder_vs_oracle():
@@ -140,8 +150,10 @@ def test_loop_and_decode_vs_oracle(variant, hw, T):
     lat_ref = restate.ddim_loop(sd, cond.double(), noise.double(), T, variant)
     z_ref = restate.decode_logits(sd, lat_ref)
     outs = {}
-    for name, kw in (("graph", dict(cuda_graph=True)), ("eager", dict(cuda_graph=False)),
-                     ("simt", dict(cuda_graph=False, simt_conv=True))):
+    for name, kw in (("graph", dict(cuda_graph=True, fp8_corr=False)), ("eager", dict(cuda_graph=False, fp8_corr=False)),
+                     ("simt", dict(cuda_graph=False, simt_conv=True)), ("fp8", dict(cuda_graph=True, fp8_corr=True))):
+        if name == "fp8" and variant != "swin":
+            continue
         eng = dd.DenoiseEngine(variant, B, (h, w), chw, T, DEV, check_range=True, **kw)
         eng.load_weights(head._engine_tensors())
         eng.set_schedule(*head.scheduler.fused_coefficients(T))
@@ -151,7 +163,7 @@ def test_loop_and_decode_vs_oracle(variant, hw, T):
             assert torch.equal(z, z2) and torch.equal(depth, depth2), "run-to-run determinism"
         outs[name] = z
         scale = max(1.0, lat_ref.abs().max().item())
-        assert (lat.double().cpu() - lat_ref).abs().max().item() < 2e-4 * scale, name
+        assert (lat.double().cpu() - lat_ref).abs().max().item() < (2e-3 if name == "fp8" else 2e-4) * scale, name
         assert (z.double().cpu() - z_ref).abs().max().item() < TOL, name
         assert eng.last_launch_count == 3 + T * (14 if variant == "swin" else 12) + 2
         eng.close()
@@ -282,9 +294,10 @@ def test_producers_reject_unsupported_pyramids():
 
 
 # ------------------------------------------------------------------------------------------------ whole plugin
-def _run_plugin(case, batch=None):
+def _run_plugin(case, batch=None, fp8=True):
     g = helpers.load_golden(case)
-    m = helpers.build_mirror(g["family"], g["T"]).to(DEV)
+    m = helpers.build_mirror(g["family"], g["T"], helpers.is_trained_case(case)).to(DEV)
+    m.depth_head.fp8_corrections = fp8
     ck = helpers.weight_checksum({k: v.cpu() for k, v in m.state_dict().items()})
     assert abs(ck - float(g["z"]["weight_checksum"])) <= 1e-5 * ck, "regenerated weights differ from the golden's"
     B = batch or g["B"]
@@ -299,13 +312,16 @@ def _run_plugin(case, batch=None):
 
 
 @pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_swinl_small", "g_res50_c2", "g_swinl_c3",
-                                  "g_swinl_c5", "g_swinl_add_small", "g_mpvit_small"])
-def test_plugin_forward_matches_reference_golden(case):
-    """`Diffusion_DCbase_Model.forward(sample)` on the GPU vs the real reference's own forward (golden)."""
+                                  "g_swinl_c5", "g_swinl_add_small", "g_mpvit_small", "g_res18_trained",
+                                  "g_swinl_small_trained"])
+def test_plugin_forward_matches_reference_golden(case, parity_log):
+    """`Diffusion_DCbase_Model.forward(sample)` on the GPU vs the real reference's own forward (golden).  `*_trained`:
+    the trained-like regime (non-zero Swin relative-position tables, non-trivial BN statistics, LN / GN affines)."""
     g, m, out = _run_plugin(case)
     z = m.depth_head.last_logits.cpu()
     z_ref = torch.from_numpy(g["z"]["logits"])
     dz = (helpers.golden_view(g, "logits", z) - z_ref).abs()
+    parity_log(case, "reference golden (logits sub-sampled x%d)" % int(g["z"]["logits_stride"]), dz)
     assert dz.max().item() < TOL, f"{case}: max|dz| {dz.max().item():.3e}"
     pm = restate.parity_metrics(helpers.golden_view(g, "logits", z), z_ref, helpers.golden_view(g, "pred", out["pred"].cpu()),
                                 torch.from_numpy(g["z"]["pred"]))
@@ -318,6 +334,17 @@ def test_plugin_forward_matches_reference_golden(case):
     assert out["pred"].shape == (g["B"], 1, g["H"], g["W"]) and out["pred_init"].shape[1] == 16
     for k in ("pred_uncertainty", "pred_inter", "weight_map", "guidance", "offset", "aff", "gamma", "confidence"):
         assert out[k] is None
+
+
+@pytest.mark.parametrize("case", ["g_swinl_small", "g_swinl_c3", "g_swinl_c5", "g_swinl_small_trained"])
+def test_plugin_forward_exact_split_mode(case, parity_log):
+    """The Swin goldens again with `fp8_corrections = False`: the exact 3-pass fp16 split everywhere (the round-1 path)."""
+    g, m, out = _run_plugin(case, fp8=False)
+    z_ref = torch.from_numpy(g["z"]["logits"])
+    dz = (helpers.golden_view(g, "logits", m.depth_head.last_logits.cpu()) - z_ref).abs()
+    parity_log(case + " [exact 3-pass split]", "reference golden (logits sub-sampled x%d)" % int(g["z"]["logits_stride"]), dz)
+    assert dz.max().item() < 2e-4, f"{case}: max|dz| {dz.max().item():.3e}"
+    m.depth_head.fp8_corrections = True
 
 
 def test_full_size_c3_batch_properties():
@@ -339,24 +366,106 @@ def test_full_size_c3_batch_properties():
     assert abs(frac_clamped - float(g["z"]["frac_clamped"])) < 0.05  # random-init outputs saturate
 
 
+def _full_res_vs_restatement(family, T, B, H, W, images, parity_log, tag):
+    """The plugin at the CONFIGURED batch; images `images` compared on ALL pixels (logits, latent, condition map) with
+    the fp32 restatement (itself pinned to the real reference at 4e-6 .. 3e-5, oracle/make_golden.py)."""
+    m = helpers.build_mirror(family, T).to(DEV)
+    sample = restate.synthetic_sample(B, H, W, configs.SEED_INPUTS)
+    sample["noise"] = restate.synthetic_noise(B, H, W, configs.SEED_NOISE)
+    m.depth_head.capture_logits = m.depth_head.capture_cond = True
+    m.depth_head.check_range = True
+    with torch.no_grad():
+        out = m({k: v.to(DEV) for k, v in sample.items()})
+    z, lat, cond = (t.cpu() for t in (m.depth_head.last_logits, m.depth_head.last_latent, m.depth_head.last_cond))
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    bb = configs.FAMILIES[family]["backbone_name"]
+    for i in images:
+        one = {k: v[i:i + 1] for k, v in sample.items() if k != "noise"}
+        ref = restate.forward(sd, one, bb, T, sample["noise"][i:i + 1])
+        dz = (z[i:i + 1] - ref["logits"]).abs()
+        parity_log(f"{tag} image {i} of {B}", "fp32 restatement, all %d pixels" % dz.numel(), dz)
+        assert dz.max().item() < TOL, (tag, i, dz.max().item())
+        assert (lat[i:i + 1] - ref["latent"]).abs().max().item() < 5e-4 * ref["latent"].abs().max().item()
+        assert (cond[i:i + 1] - ref["cond"]).abs().max().item() < 1e-4 * ref["cond"].abs().max().item()
+        pm = restate.parity_metrics(z[i:i + 1], ref["logits"], out["pred"][i:i + 1].cpu(), ref["pred"])
+        assert pm["max_rel_depth_wellcond"] < TOL
+    return m, out, z
+
+
+def test_c3_full_resolution_every_pixel(parity_log):
+    """BASELINE config 3 at full resolution (Swin-L, T=20, 352 x 1216): every pixel of the decoder logit against the
+    restatement — the goldens keep 1/16 of the logits of the large cases, so a defect at odd tile coordinates would
+    pass them (round-1 VERDICT)."""
+    _full_res_vs_restatement("swinl", 20, 1, 352, 1216, [0], parity_log, "C3")
+
+
+def test_c2_at_configured_batch(parity_log):
+    """BASELINE config 2 as configured: ResNet-50, T=20, batch 8 x 228 x 304 — all 8 images, every pixel."""
+    m, out, z = _full_res_vs_restatement("res50", 20, 8, 228, 304, list(range(8)), parity_log, "C2")
+    g = helpers.load_golden("g_res50_c2")
+    assert (helpers.golden_view(g, "logits", z[:1]) - torch.from_numpy(g["z"]["logits"])).abs().max().item() < TOL
+
+
+def test_c5_at_configured_per_gpu_batch(parity_log):
+    """BASELINE config 5 as configured per GPU: Swin-L, T=50, batch 8 x 480 x 640 (64 over 8 GPUs): image 0 against the
+    real reference's golden, image 5 on every pixel against the restatement."""
+    m, out, z = _full_res_vs_restatement("swinl", 50, 8, 480, 640, [5], parity_log, "C5")
+    g = helpers.load_golden("g_swinl_c5")
+    dz = (helpers.golden_view(g, "logits", z[:1]) - torch.from_numpy(g["z"]["logits"])).abs()
+    parity_log("C5 image 0 of 8", "reference golden (logits sub-sampled x%d)" % int(g["z"]["logits_stride"]), dz)
+    assert dz.max().item() < TOL
+    assert out["pred"].shape == (8, 1, 480, 640)
+
+
 def test_vis_head_and_ddim_loss_key():
+    """`*Vis` heads (reference ..._swin_addHAHI_vis.py:130-149): `pred_inter` = inv_t of the latent after EVERY step,
+    decoded inside the captured graph (dd_denoise_decode_steps) on the fully native path — against the same loop driven
+    one step at a time through the bare operators (dd_denoiser_forward -> axpby -> dd_decode)."""
     from diffusiondepth_b200.model.registry import HEADS
     torch.manual_seed(7)
-    vis = HEADS.build(dict(type="DDIMDepthEstimate_ResVis", in_channels=[64, 128, 256, 512], inference_steps=5,
+    T = 5
+    vis = HEADS.build(dict(type="DDIMDepthEstimate_ResVis", in_channels=[64, 128, 256, 512], inference_steps=T,
                            num_train_timesteps=1000, depth_feature_dim=16, loss_cfgs=[], init_cfg=None)).eval().to(DEV)
-    base = _res_head(5).to(DEV)
+    base = _res_head(T).to(DEV)
     base.load_state_dict(vis.state_dict())
     g = torch.Generator().manual_seed(9)
     fp = [torch.randn(1, c, -(-40 // s), -(-56 // s), generator=g).to(DEV) for c, s in
           ((64, 2), (128, 4), (256, 8), (512, 16))]
     gt = (torch.rand(1, 1, 40, 56, generator=g) * 80).to(DEV)
     noise = torch.randn(1, 16, 20, 28, generator=g).to(DEV)
+    vis.capture_cond = True
     a = vis(fp, gt, gt > 0, gt_depth_map=gt, noise=noise)
     base.eval_ddim_loss = True
     b = base(fp, gt, gt > 0, gt_depth_map=gt, noise=noise)
-    assert len(a["pred_inter"]) == 5 and a["pred_inter"][0].shape == (1, 1, 40, 56)
-    assert torch.allclose(vis.last_latent, base.last_latent, rtol=1e-5, atol=1e-4)
+    assert len(a["pred_inter"]) == T and a["pred_inter"][0].shape == (1, 1, 40, 56)
+    assert torch.equal(a["pred"], a["pred_inter"][-1]) and torch.equal(a["pred"], b["pred"])
+    assert torch.equal(vis.last_latent, base.last_latent)
     assert b["ddim_loss"].dim() == 0 and torch.isfinite(b["ddim_loss"]) and b["ddim_loss"] > 0
+    # step by step through the bare operators
+    eng = vis._any_engine(1, (20, 28), (20, 28), DEV)
+    ts, cx, ce = vis.scheduler.fused_coefficients(T)
+    x, cond = noise.clone(), vis.last_cond
+    for i, (t, ca, cb) in enumerate(zip(ts, cx, ce)):
+        x = (ca * x.double() + cb * eng.denoiser_forward(cond, x, t).double()).float().contiguous()
+        d, z = eng.decode(x, want_logits=True)
+        well = (z < 6) & (z > -13)
+        rel = (a["pred_inter"][i] - d).abs() / d.abs().clamp_min(1e-6)
+        assert rel[well].max().item() < 1e-3, (i, rel[well].max().item())
+    # the Swin Vis head takes the fully native path as well (backbone included when called through the model)
+    assert HEADS.get("DDIMDepthEstimate_Swin_ADDHAHIVis").return_intermediates
+
+
+def test_vis_head_reports_range_overflow():
+    """round-1 ADVICE: an overflow in an early step must not be cleared by a later one."""
+    from diffusiondepth_b200.model.registry import HEADS
+    torch.manual_seed(7)
+    vis = HEADS.build(dict(type="DDIMDepthEstimate_ResVis", in_channels=[64, 128, 256, 512], inference_steps=3,
+                           num_train_timesteps=1000, depth_feature_dim=16, loss_cfgs=[], init_cfg=None)).eval().to(DEV)
+    g = torch.Generator().manual_seed(1)
+    fp = [torch.full((1, c, 32 // s, 48 // s), 3.0e4, device=DEV) for c, s in ((64, 1), (128, 2), (256, 4), (512, 8))]
+    gt = (torch.rand(1, 1, 64, 96, generator=g) * 80).to(DEV)
+    with pytest.raises(dd.EngineError, match="DD_ERR_RANGE"):
+        vis(fp, gt, gt > 0, gt_depth_map=gt)
 
 
 def test_range_overflow_is_reported_not_silent():

@@ -10,10 +10,13 @@ import dd_helpers as helpers
 TOL_Z = 5e-5  # fp32-vs-fp32 re-association noise on the logits (3e-5 vs fp64 over 20 steps)
 
 
-@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small"])
+@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small", "g_res18_trained",
+                                  "g_swinl_small_trained"])
 def test_oracle_reproduces_reference_golden(case):
+    """`*_trained`: the trained-like regime (oracle.configs.trainedify: random non-zero Swin relative-position tables,
+    non-trivial BatchNorm running statistics, LayerNorm / GroupNorm affines) — what released checkpoints look like."""
     g = helpers.load_golden(case)
-    m = helpers.build_mirror(g["family"], g["T"])
+    m = helpers.build_mirror(g["family"], g["T"], helpers.is_trained_case(case))
     sd = m.state_dict()
     ck = helpers.weight_checksum(sd)
     assert abs(ck - float(g["z"]["weight_checksum"])) <= 1e-6 * ck, "weights were not regenerated identically"
@@ -35,11 +38,12 @@ def test_oracle_reproduces_reference_golden(case):
         'pred_init', 'pred_inter', 'pred_uncertainty', 'weight_map'])
 
 
-@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small"])
+@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small", "g_res18_trained",
+                                  "g_swinl_small_trained"])
 def test_mirror_producers_match_reference_condition(case):
     """backbone + FPN of the product mirror (torch ops, once per image) reproduce the reference's cond map."""
     g = helpers.load_golden(case)
-    m = helpers.build_mirror(g["family"], g["T"])
+    m = helpers.build_mirror(g["family"], g["T"], helpers.is_trained_case(case))
     sample, _ = helpers.inputs_for(g)
     with torch.no_grad():
         fp = m.depth_backbone(sample["rgb"])
@@ -104,3 +108,34 @@ def test_oracle_against_live_reference_swin_head():
         z = restate.decode_logits(sd, lat)
     assert (z - cap["z"]).abs().max().item() < TOL_Z
     assert torch.allclose(restate.decode(sd, lat), out["pred"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference sources not present")
+@pytest.mark.parametrize("hw,shift", [((24, 40), 0), ((24, 40), 3), ((13, 9), 3)])
+def test_window_msa_live_reference_trained_regime(hw, shift):
+    """The reference's own ShiftWindowMSA / WindowMSA modules (backbone/swin.py:150-189, 250-325) with NON-ZERO
+    relative-position tables, padded (24x40 -> 28x42, 13x9 -> 14x14) and shifted windows, live against (a) the
+    restatement and (b) the mirror's module — the bias / mask / roll path that the `nopretrain` factory leaves at zero."""
+    mods = ref_import.reference_modules()
+    torch.manual_seed(5)
+    C, heads = 96, 3
+    ref = mods.swin.ShiftWindowMSA(embed_dims=C, num_heads=heads, window_size=7, shift_size=shift).eval()
+    from diffusiondepth_b200.model.backbone import swin as mirror_swin
+    mine = mirror_swin.ShiftWindowMSA(C, heads, 7, shift).eval() if hasattr(mirror_swin, "ShiftWindowMSA") else None
+    gen = torch.Generator().manual_seed(6)
+    with torch.no_grad():
+        ref.w_msa.relative_position_bias_table.copy_(torch.randn(169, heads, generator=gen) * 0.7)
+    x = torch.randn(2, hw[0] * hw[1], C, generator=gen)
+    with torch.no_grad():
+        want = ref(x, hw)
+    sd = {"a." + k: v for k, v in ref.state_dict().items()}
+    got = restate._shift_window_msa(sd, x, hw, "a.", heads, 7, shift)
+    assert (got - want).abs().max().item() < 2e-6 * want.abs().max().item() + 1e-6
+    if mine is not None:
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        with torch.no_grad():
+            assert (mine(x, hw) - want).abs().max().item() < 2e-6 * want.abs().max().item() + 1e-6
+    # the bias really matters in this regime
+    with torch.no_grad():
+        ref.w_msa.relative_position_bias_table.zero_()
+        assert (ref(x, hw) - want).abs().max().item() > 1e-3
