@@ -26,18 +26,23 @@ constexpr int HALO_TW = 8;
 // (profiles/README.md): the single-CTA kernel moves ~110 KB through each SM's shared-memory port per (chunk, tap) stage
 // = ~860 cycles at 128 B/clk, above the 768 cycles of tensor work -> it is shared-memory-port bound.
 // F8 = true (PAIR only): FP8 CORRECTION PRODUCTS.  The operand planes are hi = fp16(s x), a8 = e4m3(s x / 4) and
-// l8 = e4m3((s x - hi) * 512) (weights: hi = fp16(t w), w8 = e4m3(t w / 512), lw8 = e4m3((t w - hi) * 4)), and a
-// 32-channel chunk issues  D += l8 * w8 ; D += a8 * lw8  (kind::f8f6f4, K = 32 each; the power-of-two scales cancel:
-// 512 / 512 = 1, 4 / 4 = 1)  then  D += hi * hi  (kind::f16, 2 x K = 16)  into the ONE fp32 accumulator: 4 MMAs of 2
-// pass-equivalents instead of 6 MMAs of 3.  Measured (profiles/README.md round 2): on CTA pairs a K = 32 e4m3 MMA
+// l8 = e4m3((s x - hi) * 512) (weights: hi = fp16(t w), w8 = e4m3(t w / 512), lw8 = e4m3((t w - hi) * 4)), and per
+// 32 channels the issuer sends  D += l8 * w8 ; D += a8 * lw8  (kind::f8f6f4, K = 32 each; the power-of-two scales
+// cancel: 512 / 512 = 1, 4 / 4 = 1)  and  D += hi * hi  (kind::f16, 2 x K = 16)  into the ONE fp32 accumulator: 4 MMAs
+// of 2 pass-equivalents instead of 6 MMAs of 3.  The F8 mainloop works on 64-CHANNEL chunks (BK = 64): fp16 rows of
+// 128 B (128-byte swizzle), e4m3 rows of 64 B (64-byte swizzle) — with 32-channel chunks the e4m3 rows are 32 B and both
+// TMA and the MMA operand fetch run well below their rate on such rows (first version: 816 us, this layout's probe:
+// 629 us) — and its A ring is dx-granular: a unit = the three planes of ONE column-shifted strip (36 KB), consumed by
+// that dx's three taps, so three units and three 32 KB weight stages fit beside each other.  Measured (profiles/README.md round 2): on CTA pairs a K = 32 e4m3 MMA
 // costs ~175 cycles against 2 x 128 for the same K in fp16 (single CTA: 260 — it needs cta_group::2), and under the
 // 1 kW power cap the clock rises with the lighter MMA mix: 256->256 at C3 629 us vs 948 us (3 fp16 passes on pairs)
 // vs 1119 us (round 1).  Parity cost (oracle/probe_fp8_static.py, real C3 case vs the reference golden): max |dz|
 // 3.4e-4 / rms 7e-5 instead of 2.3e-5 / 4.5e-6, tolerance 1e-3.  Same bytes per element in HBM (2 + 1 + 1).
 template <int CIN, int COUT, int BK, bool PAIR = false, bool F8 = false>
 struct HaloCfg {
-  static_assert(!F8 || (PAIR && BK == 32 && COUT == 256), "fp8 corrections: pair kernel, 32-channel chunks, wide layers");
-  static_assert((CIN % BK == 0 || CIN < BK) && CIN % 16 == 0 && (BK == 16 || BK == 32), "bad K chunk");
+  static_assert(!F8 || (PAIR && BK == 64 && COUT == 256 && CIN % 64 == 0), "fp8 corrections: pair kernel, 64-channel chunks, wide layers");
+  static_assert(F8 || BK == 16 || BK == 32, "bad K chunk");
+  static_assert((CIN % BK == 0 || CIN < BK) && CIN % 16 == 0, "bad K chunk");
   // CIN < BK (16-channel latent, BK = 32) is supported — the box is wider than the channel extent, TMA zero-fills the
   // rest and only CIN / 16 K-steps are issued — but measured slower on 16->64 (110 vs 82 us), so the engine keeps BK = 16.
   static constexpr int KC = (CIN + BK - 1) / BK;
@@ -49,14 +54,14 @@ struct HaloCfg {
   static constexpr int STRIP8_BYTES = STRIP_ROWS * BK;              // e4m3 plane: one byte per channel
   static constexpr int STRIP8_PAD = (STRIP8_BYTES + 1023) / 1024 * 1024;
   static constexpr int DX_STRIDE = F8 ? STRIP_PAD + 2 * STRIP8_PAD : 2 * STRIP_PAD;  // planes of one dx: hi, lo | hi, a8, l8
-  static constexpr int A_SLOT = 3 * DX_STRIDE;
+  static constexpr int A_SLOT = F8 ? DX_STRIDE : 3 * DX_STRIDE;       // F8: one dx per ring unit
   static constexpr int B_ROWS = PAIR ? COUT / 2 : COUT;             // weight rows this CTA stages
   static constexpr int B_TILE = B_ROWS * ROW_BYTES;                 // one plane, one tap, one chunk
   static constexpr int B_TILE_PAD = (B_TILE + 1023) / 1024 * 1024;
   static constexpr int B8_TILE = B_ROWS * BK;
   static constexpr int B8_TILE_PAD = (B8_TILE + 1023) / 1024 * 1024;
   static constexpr int B_SLOT = F8 ? B_TILE_PAD + 2 * B8_TILE_PAD : 2 * B_TILE_PAD;
-  static constexpr int A_SLOTS = 2;
+  static constexpr int A_SLOTS = F8 ? 3 : 2;
   // Two sets of four epilogue warps where the epilogue is on the critical path: Cout = 64 (two chunks, one per set; each
   // set then owns two GroupNorm groups) and the pair kernel's 64->256 layer (K = 576: 18 stages per tile, so draining a
   // 128 x 256 fp32 tile with one warp per scheduler took as long as the mainloop; the sets take alternate chunks and
@@ -65,17 +70,18 @@ struct HaloCfg {
   static constexpr bool STATS_LOCAL = (COUT == 64);  // a set's chunk(s) cover whole groups of their own
   static constexpr int EPI_WARPS = 4 * EPI_SETS;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
-  static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;
+  static constexpr int XPOSE_BYTES = F8 ? 0 : EPI_WARPS * 32 * 32 * 4;  // F8: fp32 outputs (tests) store row-wise
   static constexpr int BUDGET = 227 * 1024 - 1024 - 1024 - XPOSE_BYTES - A_SLOTS * A_SLOT;
   static constexpr int B_SLOTS_RAW = BUDGET / B_SLOT;
   // Small layers (16->64, 64->16): all 9 x KC weight tiles fit in shared memory -> fetch them ONCE per CTA instead of once
   // per tile.  Each cp.async.bulk.tensor costs its issuing thread ~160 ns, and 18 weight copies per 128-pixel tile were
   // the whole tile time of the 16->64 layer (tensor pipe 12.5 % active).
   static constexpr bool B_RESIDENT = !PAIR && (9 * KC * B_SLOT <= 40 * 1024) && (9 * KC <= B_SLOTS_RAW);
-  static constexpr int B_SLOTS = B_RESIDENT ? 9 * KC : (B_SLOTS_RAW > 8 ? 8 : B_SLOTS_RAW);
+  static constexpr int B_SLOTS = B_RESIDENT ? 9 * KC : (F8 ? 3 : (B_SLOTS_RAW > 8 ? 8 : B_SLOTS_RAW));
+  static_assert(!F8 || B_SLOTS_RAW >= 3, "fp8 layout does not fit");
   static_assert(B_SLOTS >= 2, "B ring too small");
   static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 1024 + XPOSE_BYTES;
-  static constexpr int A_TX = F8 ? 3 * (STRIP_BYTES + 2 * STRIP8_BYTES) : 6 * STRIP_BYTES;
+  static constexpr int A_TX = F8 ? STRIP_BYTES + 2 * STRIP8_BYTES : 6 * STRIP_BYTES;
   static constexpr int B_TX = F8 ? B_TILE + 2 * B8_TILE : 2 * B_TILE;
   // Narrow-N layers: back-to-back MMAs into ONE accumulator serialise on its read-modify-write latency (~105 cycles
   // per MMA measured for N = 64 / 16, vs 32-48 cycles of work).  Give each of the three split passes its own TMEM
@@ -167,6 +173,30 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const bool leader = elect_one();
     int sa = 0;
     uint32_t pa = 0;
+    if constexpr (F8) {
+      DD_TILE_LOOP {
+        const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * HALO_TW, y0 = ty * HALO_TH;
+        for (int kc = 0; kc < C::KC; ++kc) {
+          for (int dx = 0; dx < 3; ++dx) {  // one ring unit per column-shifted strip: hi, a8, l8
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            uint8_t* d = a_ring + sa * C::A_SLOT;
+            if (leader) {
+              const uint32_t lead = mapa_u32(smem_u32(&a_full[sa]), 0);
+              mbar_arrive_expect_tx_cluster(lead, C::A_TX);
+              tma_load_4d_pair(d, &tmA_hi, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+              tma_load_4d_pair(d + C::STRIP_PAD, &tmA_lo, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+              tma_load_4d_pair(d + C::STRIP_PAD + C::STRIP8_PAD, &tmA_x, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
+            }
+            __syncwarp();
+            if (++sa == C::A_SLOTS) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+        }
+      }
+    } else
     DD_TILE_LOOP {
       const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
       const int x0 = tx * HALO_TW, y0 = ty * HALO_TH;
@@ -182,8 +212,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               uint8_t* d = s + dx * C::DX_STRIDE;
               tma_load_4d_pair(d, &tmA_hi, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
               tma_load_4d_pair(d + C::STRIP_PAD, &tmA_lo, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
-              if constexpr (F8)
-                tma_load_4d_pair(d + C::STRIP_PAD + C::STRIP8_PAD, &tmA_x, lead, kc * BK, x0 + dx - 1, y0 - 1, img);
             }
           } else {
             mbar_arrive_expect_tx(&a_full[sa], C::A_TX);
@@ -209,7 +237,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     DD_TILE_LOOP {
       if (C::B_RESIDENT && tile != static_cast<int>(blockIdx.x)) break;  // weights stay in their slots after the first tile
       for (int kc = 0; kc < C::KC; ++kc) {
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int it = 0; it < 9; ++it) {
+          const int tap = F8 ? (it % 3) * 3 + it / 3 : it;  // F8 walks the taps dx-major (dx = it / 3, dy = it % 3)
           mbar_wait(&b_empty[sb], pb ^ 1);
           uint8_t* s = b_ring + sb * C::B_SLOT;
           if (leader) {

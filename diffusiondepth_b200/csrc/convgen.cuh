@@ -34,12 +34,17 @@ struct GenConvArgs {
   int* status;
 };
 
-template <int NT>
+// PAIR = true: two CTAs of one cluster run ONE tcgen05.mma.cta_group::2 with M = 256 (two consecutive M tiles, one per
+// CTA) and each stages only HALF of the weight tile (NT / 2 rows).  Per 32-channel stage a single CTA pulls
+// 2 * (128 + NT) * 64 B from L2 for 3 * NT cycles of MMA work = 64 B/clk at NT = 256, above the ~40 B/clk an SM gets from
+// L2 when all 148 stream at once (profiles/README.md round 2); a pair needs 2 * (128 + NT / 2) * 64 B = 42 B/clk.
+template <int NT, bool PAIR = false>
 struct GenCfg {
   static constexpr int BK = 32;
   static constexpr int ROW_BYTES = BK * 2;
   static constexpr int A_BYTES = TILE_M * ROW_BYTES;  // 8 KB per plane
-  static constexpr int B_BYTES = NT * ROW_BYTES;
+  static constexpr int B_ROWS = PAIR ? NT / 2 : NT;   // weight rows this CTA stages
+  static constexpr int B_BYTES = B_ROWS * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
   static constexpr int EPI_WARPS = 8;
   static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;  // per-warp 32x32 fp32 transpose tile (XOR-swizzled)
@@ -51,13 +56,14 @@ struct GenCfg {
   static_assert(NT % 32 == 0 && NT <= 256 && 2 * NT <= 512, "bad N tile");  // instantiated: 64, 128, 192, 256
 };
 
-template <int NT>
+// PAIR: launched as clusters of 2; work item = (pair of M tiles, N tile); tmB_* then have a box of NT / 2 rows.
+template <int NT, bool PAIR = false>
 __global__ void __launch_bounds__(384, 1)
 convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_constant__ CUtensorMap tmA0_lo,
                     const __grid_constant__ CUtensorMap tmA1_hi, const __grid_constant__ CUtensorMap tmA1_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const GenConvArgs p) {
-  using C = GenCfg<NT>;
+  using C = GenCfg<NT, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -71,7 +77,13 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
   const int lane = threadIdx.x & 31;
   const int kc_total = p.kc0 + p.kc1;
   const int k_iters = p.taps * kc_total;
-  const int num_work = p.m_tiles * p.n_tiles;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // cluster dims (2,1,1): rank == blockIdx.x & 1
+  // PAIR: both CTAs of a pair walk the same work items (pair of M tiles 2 * mp + rank, N tile); an M tile past the end is
+  // computed on zero-filled (out-of-bounds) patches and never stored
+  const int m_units = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int num_work = m_units * p.n_tiles;
+  const int work0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int work_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0_hi);
@@ -79,21 +91,28 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
     tma_prefetch_desc(&tmB_hi);
     tma_prefetch_desc(&tmB_lo);
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full_bar[s], 2);  // two producer threads (activation planes / weight planes) arrive per stage
+      // two producers (activation planes / weight planes) arrive per stage; pair mode: those of both CTAs, on the
+      // leader's barrier.  empty / tfull barriers live in each CTA and are hit by multicast commits.
+      mbar_init(&full_bar[s], PAIR ? 4 : 2);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 8);  // eight epilogue warps
+      mbar_init(&tempty_bar[b], PAIR ? 16 : 8);  // eight epilogue warps (of both CTAs, on the leader's barrier)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
@@ -105,8 +124,10 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
     const bool leader = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      const int nt = work % p.n_tiles, mt = work / p.n_tiles;  // n fastest: neighbours share the A patch in L2
+    for (int work = work0; work < num_work; work += work_step) {
+      const int nt = work % p.n_tiles;  // n fastest: neighbours share the A patch in L2
+      const int mt = (PAIR ? 2 * (work / p.n_tiles) + static_cast<int>(rank) : work / p.n_tiles);
+      // an M tile past the end (second CTA of the last pair): image index = B -> every row is out of bounds -> zero fill
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
       const int x0 = tx * TILE_W, y0 = ty * TILE_H;
       for (int tap = 0; tap < p.taps; ++tap) {
@@ -116,7 +137,23 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           uint8_t* s = stage_ptr(stage);
           const int ax = x0 * p.stride + dx, ay = y0 * p.stride + dy;
           if (leader) {
-            if (!act) {
+            if constexpr (PAIR) {
+              const uint32_t lead = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              const int brow = nt * NT + static_cast<int>(rank) * C::B_ROWS;  // this CTA's half of the N tile
+              if (!act) {
+                mbar_arrive_expect_tx_cluster(lead, 2 * C::B_BYTES);
+                tma_load_3d_pair(s + 2 * C::A_BYTES, &tmB_hi, lead, kc * C::BK, brow, tap);
+                tma_load_3d_pair(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, lead, kc * C::BK, brow, tap);
+              } else if (kc < p.kc0) {
+                mbar_arrive_expect_tx_cluster(lead, 2 * C::A_BYTES);
+                tma_load_4d_pair(s, &tmA0_hi, lead, kc * C::BK, ax, ay, img);
+                tma_load_4d_pair(s + C::A_BYTES, &tmA0_lo, lead, kc * C::BK, ax, ay, img);
+              } else {
+                mbar_arrive_expect_tx_cluster(lead, 2 * C::A_BYTES);
+                tma_load_4d_pair(s, &tmA1_hi, lead, (kc - p.kc0) * C::BK, ax, ay, img);
+                tma_load_4d_pair(s + C::A_BYTES, &tmA1_lo, lead, (kc - p.kc0) * C::BK, ax, ay, img);
+              }
+            } else if (!act) {
               mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_BYTES);
               tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * C::BK, nt * NT, tap);
               tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * C::BK, nt * NT, tap);
@@ -138,15 +175,15 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // the whole warp walks the loop (waits and operand addresses stay warp-uniform -> uniform registers, MMAs issued
-    // back to back); one elected lane issues the MMAs and commits (see conv_halo.cuh)
+    // back to back); one elected lane issues the MMAs and commits (see conv_halo.cuh).  Pair mode: the leader CTA only.
     const bool leader = elect_one();
-    constexpr uint32_t idesc = umma_idesc_f16(TILE_M, NT);
+    constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, NT);
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
     int buf = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    for (int work = work0; work < num_work; work += work_step) {
       mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * NT);
@@ -165,12 +202,23 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           const uint64_t b_hi = umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES);
           const uint64_t b_lo = umma_smem_desc(sb_lo + k * 32, C::ROW_BYTES);
           // neighbours share an operand (B_hi, then A_hi); see conv_halo.cuh
-          umma_f16(d_tmem, a_lo, b_hi, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
-          umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+          if constexpr (PAIR) {
+            umma_f16_pair(d_tmem, a_lo, b_hi, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_f16_pair(d_tmem, a_hi, b_hi, idesc, 1u);
+            umma_f16_pair(d_tmem, a_hi, b_lo, idesc, 1u);
+          } else {
+            umma_f16(d_tmem, a_lo, b_hi, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+            umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+          }
         }
-        umma_commit(&empty_bar[stage]);
-        if (it == k_iters - 1) umma_commit(&tfull_bar[buf]);
+        if constexpr (PAIR) {
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (it == k_iters - 1) umma_commit_pair(&tfull_bar[buf], 3);
+        } else {
+          umma_commit(&empty_bar[stage]);
+          if (it == k_iters - 1) umma_commit(&tfull_bar[buf]);
+        }
         }  // leader
         __syncwarp();
         if (++stage == C::STAGES) {
@@ -197,11 +245,12 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
     bool overflow = false;
     const int cq = p.cout >> 2;
     constexpr int NCH = NT / 32;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      const int nt = work % p.n_tiles, mt = work / p.n_tiles;
+    for (int work = work0; work < num_work; work += work_step) {
+      const int nt = work % p.n_tiles;
+      const int mt = (PAIR ? 2 * (work / p.n_tiles) + static_cast<int>(rank) : work / p.n_tiles);
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, img = mt / (p.tiles_x * p.tiles_y);
       const int x = tx * TILE_W + c, y = ty * TILE_H + r;
-      const bool valid = (x < p.W) && (y < p.H) && (p.m_valid <= 0 || (y * p.W + x) < p.m_valid);
+      const bool valid = (mt < p.m_tiles) && (x < p.W) && (y < p.H) && (p.m_valid <= 0 || (y * p.W + x) < p.m_valid);
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       // element offset of this lane's row at channel 0 (non-shuffle) -- fits 32 bits for every tensor we produce
       const uint32_t row_base = static_cast<uint32_t>(((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout);
@@ -302,17 +351,20 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+        else mbar_arrive(&tempty_bar[buf]);
+      }
       buf ^= 1;
     }
     if (overflow) atomicOr(p.status, 1);
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 

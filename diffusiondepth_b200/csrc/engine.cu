@@ -192,6 +192,14 @@ cudaError_t configure_all_kernels() {
   if ((e = configure_umma_all_epi<256, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<256, 64, 64>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<64, 16, 64>()) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::GenCfg<256, true>::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<192, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::GenCfg<192, true>::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::GenCfg<128, true>::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::GenCfg<64, true>::SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 dd::GenCfg<256>::SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dd::convgen_umma_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -357,6 +365,7 @@ struct GenLayer {
   float* shift = nullptr;
   float wscale = 1.f;
   CUtensorMap mb_hi, mb_lo;
+  CUtensorMap mp_hi, mp_lo;  // box of nt / 2 rows: each CTA of a pair stages half of the N tile
 };
 struct Planes {
   __half* hi = nullptr;
@@ -371,6 +380,7 @@ struct Gemm {  // Linear layer on the tensor-core GEMM path: W [N][K] as fp16 hi
   CUtensorMap mb_hi, mb_lo;          // box {32, nt}
   bool alt = false;                  // N tiles by both 256 and 192: second pair of maps for the other width
   CUtensorMap mb_hi_alt, mb_lo_alt;  // box {32, 192}
+  CUtensorMap mp_hi, mp_lo, mp_hi_alt, mp_lo_alt;  // the same with boxes of nt / 2 rows (CTA pairs)
 };
 struct SwinBlockW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *table = nullptr;
@@ -426,6 +436,7 @@ struct dd_engine {
   // tuning / timing probes: read from the environment ONCE in dd_create, and only in a -DDD_PROBES build
   // (profiles/README.md); a product build ignores the variables altogether
   int probe_fp8 = 0, swap_mask = -1, halo_mask = -1, pair_mask = -1;
+  int genpair_mask = 1;  // DD_GENPAIR=0 (probes build): producer convs / GEMMs on single CTAs
   bool want_clk_probe = false;
   bool weights_ready = false;
   std::map<std::string, Raw> raw;
@@ -1104,6 +1115,8 @@ int pack_gen(dd_engine* e, GenLayer& L, const std::string& wkey, const std::stri
   CUDA_TRY(cudaStreamSynchronize(st));
   if ((rc = make_wgen_map(&L.mb_hi, L.w_hi, L.cout, cp, L.taps, L.nt))) return rc;
   if ((rc = make_wgen_map(&L.mb_lo, L.w_lo, L.cout, cp, L.taps, L.nt))) return rc;
+  if ((rc = make_wgen_map(&L.mp_hi, L.w_hi, L.cout, cp, L.taps, L.nt / 2))) return rc;
+  if ((rc = make_wgen_map(&L.mp_lo, L.w_lo, L.cout, cp, L.taps, L.nt / 2))) return rc;
   return DD_OK;
 }
 
@@ -1131,18 +1144,45 @@ int pack_producers(dd_engine* e, cudaStream_t st, float* scratch) {
   return DD_OK;
 }
 
-template <int NT>
-void launch_gen(int grid, cudaStream_t st, const CUtensorMap& m0h, const CUtensorMap& m0l, const CUtensorMap& m1h,
-                const CUtensorMap& m1l, const CUtensorMap& bh, const CUtensorMap& bl, const dd::GenConvArgs& a) {
-  dd::convgen_umma_kernel<NT><<<grid, 384, dd::GenCfg<NT>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, bh, bl, a);
+template <int NT, bool PAIR>
+cudaError_t launch_gen(int grid, cudaStream_t st, const CUtensorMap& m0h, const CUtensorMap& m0l, const CUtensorMap& m1h,
+                       const CUtensorMap& m1l, const CUtensorMap& bh, const CUtensorMap& bl, const dd::GenConvArgs& a) {
+  if constexpr (!PAIR) {
+    dd::convgen_umma_kernel<NT, false><<<grid, 384, dd::GenCfg<NT, false>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, bh, bl, a);
+    return cudaGetLastError();
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = dd::GenCfg<NT, true>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, dd::convgen_umma_kernel<NT, true>, m0h, m0l, m1h, m1l, bh, bl, a);
+  }
 }
-void launch_gen_nt(int nt, int grid, cudaStream_t st, const CUtensorMap& m0h, const CUtensorMap& m0l, const CUtensorMap& m1h,
-                   const CUtensorMap& m1l, const CUtensorMap& bh, const CUtensorMap& bl, const dd::GenConvArgs& a) {
+// m_tiles x n_tiles work items of one producer conv / GEMM -> (use CTA pairs?, grid size).  Pairs (M = 256 per
+// tcgen05.mma, half the weight bytes per SM) whenever there are at least two M tiles and the engine allows it.
+bool gen_use_pair(const dd_engine* e, int m_tiles) {
+  return (e->cfg.flags & DD_FLAG_PAIR_WIDE) && !(e->cfg.flags & DD_FLAG_SIMT_CONV) && m_tiles >= 2 && e->genpair_mask != 0;
+}
+int gen_grid(const dd_engine* e, bool pair, int m_tiles, int n_tiles) {
+  if (!pair) return std::min(m_tiles * n_tiles, e->sm_count);
+  return std::min(2 * ((m_tiles + 1) / 2) * n_tiles, e->sm_count & ~1);
+}
+cudaError_t launch_gen_nt(int nt, bool pair, int grid, cudaStream_t st, const CUtensorMap& m0h, const CUtensorMap& m0l,
+                          const CUtensorMap& m1h, const CUtensorMap& m1l, const CUtensorMap& bh, const CUtensorMap& bl,
+                          const dd::GenConvArgs& a) {
   switch (nt) {
-    case 256: launch_gen<256>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a); break;
-    case 192: launch_gen<192>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a); break;
-    case 128: launch_gen<128>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a); break;
-    default: launch_gen<64>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a); break;
+    case 256: return pair ? launch_gen<256, true>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a) : launch_gen<256, false>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a);
+    case 192: return pair ? launch_gen<192, true>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a) : launch_gen<192, false>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a);
+    case 128: return pair ? launch_gen<128, true>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a) : launch_gen<128, false>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a);
+    default: return pair ? launch_gen<64, true>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a) : launch_gen<64, false>(grid, st, m0h, m0l, m1h, m1l, bh, bl, a);
   }
 }
 
@@ -1192,11 +1232,11 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
     m1h = m0h;
     m1l = m0l;
   }
-  const int work = a.m_tiles * a.n_tiles;
-  const int grid = work < e->sm_count ? work : e->sm_count;
-  launch_gen_nt(L.nt, grid, st, m0h, m0l, m1h, m1l, L.mb_hi, L.mb_lo, a);
+  const bool pair = gen_use_pair(e, a.m_tiles);
+  const int grid = gen_grid(e, pair, a.m_tiles, a.n_tiles);
+  const cudaError_t err = launch_gen_nt(L.nt, pair, grid, st, m0h, m0l, m1h, m1l, pair ? L.mp_hi : L.mb_hi,
+                                        pair ? L.mp_lo : L.mb_lo, a);
   e->launches++;
-  cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("convgen launch: ") + cudaGetErrorString(err));
   return DD_OK;
 }
@@ -1327,10 +1367,14 @@ int pack_gemm(dd_engine* e, Gemm& G, const std::string& wkey, const std::string&
   CUDA_TRY(cudaGetLastError());
   if ((rc = make_wgen_map(&G.mb_hi, G.w_hi, N, K, 1, G.nt))) return rc;
   if ((rc = make_wgen_map(&G.mb_lo, G.w_lo, N, K, 1, G.nt))) return rc;
+  if ((rc = make_wgen_map(&G.mp_hi, G.w_hi, N, K, 1, G.nt / 2))) return rc;
+  if ((rc = make_wgen_map(&G.mp_lo, G.w_lo, N, K, 1, G.nt / 2))) return rc;
   G.alt = (G.nt == 256 && N % 192 == 0);
   if (G.alt) {
     if ((rc = make_wgen_map(&G.mb_hi_alt, G.w_hi, N, K, 1, 192))) return rc;
     if ((rc = make_wgen_map(&G.mb_lo_alt, G.w_lo, N, K, 1, 192))) return rc;
+    if ((rc = make_wgen_map(&G.mp_hi_alt, G.w_hi, N, K, 1, 96))) return rc;
+    if ((rc = make_wgen_map(&G.mp_lo_alt, G.w_lo, N, K, 1, 96))) return rc;
   }
   return DD_OK;
 }
@@ -1386,13 +1430,15 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   a.tiles_y = (a.H + dd::TILE_H - 1) / dd::TILE_H;
   a.m_tiles = a.tiles_y;
   // wave quantisation: with few M tiles (deep Swin stages) pick the N-tile width whose last wave wastes least
+  const bool pair = gen_use_pair(e, a.m_tiles);
+  const int units = pair ? (a.m_tiles + 1) / 2 : a.m_tiles, slots = pair ? e->sm_count / 2 : e->sm_count;
   int nt = G.nt;
   if (G.alt) {
-    auto cost = [&](int w) { return ((a.m_tiles * (G.N / w) + e->sm_count - 1) / e->sm_count) * w; };
+    auto cost = [&](int w) { return ((units * (G.N / w) + slots - 1) / slots) * w; };
     if (cost(192) < cost(256)) nt = 192;
   }
-  const CUtensorMap& mbh = (nt == G.nt) ? G.mb_hi : G.mb_hi_alt;
-  const CUtensorMap& mbl = (nt == G.nt) ? G.mb_lo : G.mb_lo_alt;
+  const CUtensorMap& mbh = pair ? ((nt == G.nt) ? G.mp_hi : G.mp_hi_alt) : ((nt == G.nt) ? G.mb_hi : G.mb_hi_alt);
+  const CUtensorMap& mbl = pair ? ((nt == G.nt) ? G.mp_lo : G.mp_lo_alt) : ((nt == G.nt) ? G.mb_lo : G.mb_lo_alt);
   a.n_tiles = G.N / nt;
   a.kc0 = G.K / 32;
   a.kc1 = 0;
@@ -1415,14 +1461,9 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   int rc;
   if ((rc = make_act_map(&mh, A.hi, 1, a.H, 16, G.K, 32))) return rc;
   if ((rc = make_act_map(&ml, A.lo, 1, a.H, 16, G.K, 32))) return rc;
-  const int work = a.m_tiles * a.n_tiles;
-  const int grid = work < e->sm_count ? work : e->sm_count;
-  if (nt == 256)
-    dd::convgen_umma_kernel<256><<<grid, 384, dd::GenCfg<256>::SMEM_BYTES, st>>>(mh, ml, mh, ml, mbh, mbl, a);
-  else
-    dd::convgen_umma_kernel<192><<<grid, 384, dd::GenCfg<192>::SMEM_BYTES, st>>>(mh, ml, mh, ml, mbh, mbl, a);
+  const int grid = gen_grid(e, pair, a.m_tiles, a.n_tiles);
+  const cudaError_t err = launch_gen_nt(nt, pair, grid, st, mh, ml, mh, ml, mbh, mbl, a);
   e->launches++;
-  cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(err));
   return DD_OK;
 }
@@ -1536,6 +1577,7 @@ int dd_create(const dd_config* cfg, dd_handle* out) {
   if (const char* v = getenv("DD_SWAP_MASK")) e->swap_mask = atoi(v);
   if (const char* v = getenv("DD_HALO_MASK")) e->halo_mask = atoi(v);
   if (const char* v = getenv("DD_PAIR_MASK")) e->pair_mask = atoi(v);
+  if (const char* v = getenv("DD_GENPAIR")) e->genpair_mask = atoi(v);
   e->want_clk_probe = getenv("DD_CLK_PROBE") != nullptr;
 #endif
   if (cudaMallocHost(&e->status_host, 64) != cudaSuccess ||
@@ -2074,6 +2116,8 @@ int dd_bench_gemm(dd_handle h, int32_t M, int32_t K, int32_t N, int32_t mode, in
   int rc;
   if ((rc = make_wgen_map(&G.mb_hi, G.w_hi, N, K, 1, G.nt))) return rc;
   if ((rc = make_wgen_map(&G.mb_lo, G.w_lo, N, K, 1, G.nt))) return rc;
+  if ((rc = make_wgen_map(&G.mp_hi, G.w_hi, N, K, 1, G.nt / 2))) return rc;
+  if ((rc = make_wgen_map(&G.mp_lo, G.w_lo, N, K, 1, G.nt / 2))) return rc;
   int* saved = h->status;
   h->status = status;
   auto once = [&]() {

@@ -43,6 +43,48 @@ def gather_depth(pred_local: torch.Tensor, global_batch: int, group=None) -> tor
     return torch.cat([out[r * cmax:r * cmax + c] for r, c in enumerate(counts)])
 
 
+class DepthGatherer:
+    """The same single collective, taken OFF the compute stream for steady-state serving: `submit()` enqueues the
+    all-gather of this step's maps on a side stream into one of `slots` rotating result buffers and returns at once, so
+    the next step's kernels never queue behind a peer that is still finishing the current one (under a power cap the
+    ranks' step times differ by a few per cent; a blocking per-step collective makes every rank run at the pace of that
+    step's slowest peer — round-1 SCALE: 0.95 at N = 8).  `result(ticket)` makes the current stream wait for that
+    gather.  On CPU tensors (gloo tests) it degrades to the synchronous call."""
+
+    def __init__(self, global_batch: int, group=None, slots: int = 2):
+        self.global_batch, self.group, self.slots = global_batch, group, max(2, int(slots))
+        self._bufs, self._done, self._stream, self._n = [None] * self.slots, [None] * self.slots, None, 0
+
+    def submit(self, pred_local: torch.Tensor) -> int:
+        slot = self._n % self.slots
+        self._n += 1
+        if not pred_local.is_cuda:
+            self._bufs[slot] = gather_depth(pred_local, self.global_batch, self.group)
+            return slot
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=pred_local.device)
+        cur = torch.cuda.current_stream(pred_local.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self._stream.wait_event(ready)
+        with torch.cuda.stream(self._stream):
+            self._bufs[slot] = gather_depth(pred_local, self.global_batch, self.group)
+            done = torch.cuda.Event()
+            done.record(self._stream)
+        pred_local.record_stream(self._stream)  # the allocator must not hand these maps out before the gather has read them
+        self._done[slot] = done
+        return slot
+
+    def result(self, ticket: int) -> torch.Tensor:
+        if self._done[ticket] is not None:
+            torch.cuda.current_stream(self._bufs[ticket].device).wait_event(self._done[ticket])
+        return self._bufs[ticket]
+
+    def drain(self):
+        if self._stream is not None:
+            torch.cuda.current_stream(self._stream.device).wait_stream(self._stream)
+
+
 def run_sharded(model: Callable[[Dict[str, torch.Tensor]], Dict[str, torch.Tensor]], sample: Dict[str, torch.Tensor],
                 global_batch: int, group=None) -> torch.Tensor:
     """Each rank runs `model` on its slice of the full-batch `sample`, then one all-gather of 'pred'."""

@@ -37,10 +37,12 @@ _PARITY = []
 def parity_log():
     """Record the margin a parity test measured (max / RMS |dz| on the decoder logit == relative depth error); the
     session writes them to gpurun_out/parity_margins.json (copied to profiles/PARITY_rNN.json per round)."""
-    def log(case, against, dz):
+    def log(case, against, dz, **extra):
         dz = dz.double().flatten()
-        _PARITY.append({"case": case, "against": against, "max_dz": float(dz.max()), "rms_dz": float(dz.pow(2).mean().sqrt()),
-                        "n": int(dz.numel()), "tolerance": 1e-3})
+        row = {"case": case, "against": against, "max_dz": float(dz.max()), "rms_dz": float(dz.pow(2).mean().sqrt()),
+               "n": int(dz.numel()), "tolerance": 1e-3, **extra}
+        _PARITY.append(row)
+        print("\n[parity] " + " ".join(f"{k}={v:.3e}" if isinstance(v, float) else f"{k}={v}" for k, v in row.items()))
     return log
 
 

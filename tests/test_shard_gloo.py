@@ -42,7 +42,15 @@ def _worker(rank, world, port, gb, q):
 
         out = shard.run_sharded(fake_model, full, gb)
         want = full["rgb"].mean(1, keepdim=True) * 2 + 1
-        q.put((rank, bool(torch.equal(out, want)), tuple(out.shape)))
+        ok = bool(torch.equal(out, want))
+        # the off-stream, double-buffered variant used for steady-state serving (synchronous on CPU tensors)
+        first, count = shard.shard_range(gb, rank, world)
+        gat = shard.DepthGatherer(gb)
+        tickets = [gat.submit(fake_model(shard.slice_sample(full, first, count))["pred"] + i) for i in range(3)]
+        ok &= tickets == [0, 1, 0] and bool(torch.equal(gat.result(tickets[1]), want + 1))
+        ok &= bool(torch.equal(gat.result(tickets[2]), want + 2))
+        gat.drain()
+        q.put((rank, ok, tuple(out.shape)))
     finally:
         dist.destroy_process_group()
 
