@@ -273,6 +273,64 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, COUT);
     int sa = 0, sb = 0, buf = 0;
     uint32_t pa = 0, pb = 0, acc_phase = 0;
+    if constexpr (F8) {
+      // 64-channel chunks; per (chunk, dx) one A unit {hi: 128-byte rows, a8 / l8: 64-byte rows}, per (chunk, dx, dy) one
+      // weight stage {hi, w8, lw8}.  Tap (dy, dx) = the unit advanced dy rows: 8 pixels x row bytes = exactly one swizzle
+      // repeat of either layout, so the canonical K-major descriptors still apply.  8 MMAs per stage: the e4m3 correction
+      // products first (2 x K = 32 per plane pair), then hi * hi (4 x K = 16).
+      constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) |
+                                  (static_cast<uint32_t>((2 * TILE_M) >> 4) << 24);  // D f32, A / B e4m3, M = 256
+      DD_TILE_LOOP {
+        mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS);
+        for (int kc = 0; kc < C::KC; ++kc) {
+          for (int dx = 0; dx < 3; ++dx) {
+            mbar_wait(&a_full[sa], pa);
+            const uint32_t a_base = smem_u32(a_ring + sa * C::A_SLOT);
+            for (int dy = 0; dy < 3; ++dy) {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint32_t sa_hi = a_base + dy * HALO_TW * C::ROW_BYTES;
+              const uint32_t sa_a8 = a_base + C::STRIP_PAD + dy * HALO_TW * BK;
+              const uint32_t sa_l8 = sa_a8 + C::STRIP8_PAD;
+              const uint32_t sb_hi = smem_u32(b_ring + sb * C::B_SLOT);
+              const uint32_t sb_w8 = sb_hi + C::B_TILE_PAD;
+              const uint32_t sb_lw8 = sb_w8 + C::B8_TILE_PAD;
+              if (leader) {
+#pragma unroll
+                for (int k = 0; k < BK / 32; ++k) {
+                  umma_f8_pair(d_tmem, umma_smem_desc(sa_l8 + k * 32, BK), umma_smem_desc(sb_w8 + k * 32, BK), idesc8,
+                               (kc | dx | dy | k) != 0 ? 1u : 0u);
+                  umma_f8_pair(d_tmem, umma_smem_desc(sa_a8 + k * 32, BK), umma_smem_desc(sb_lw8 + k * 32, BK), idesc8, 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  umma_f16_pair(d_tmem, umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES),
+                                umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES), idesc, 1u);
+                umma_commit_pair(&b_empty[sb], 3);
+              }
+              __syncwarp();
+              if (++sb == C::B_SLOTS) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+            if (leader) {
+              umma_commit_pair(&a_empty[sa], 3);
+              if (kc == C::KC - 1 && dx == 2) umma_commit_pair(&tfull_bar[buf], 3);
+            }
+            __syncwarp();
+            if (++sa == C::A_SLOTS) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+        }
+        acc_phase ^= (1u << buf);
+        buf ^= 1;
+      }
+    } else
     DD_TILE_LOOP {
       mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
       tc_fence_after();
@@ -286,24 +344,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           tc_fence_after();
           // strip dx, dy rows down: 8-pixel groups stay dense (8 * ROW_BYTES) and aligned to the swizzle repeat
           const uint32_t sa_hi = a_base + dx * C::DX_STRIDE + dy * HALO_TW * C::ROW_BYTES;
-          const uint32_t sa_lo = a_base + dx * C::DX_STRIDE + C::STRIP_PAD + dy * HALO_TW * (F8 ? BK : C::ROW_BYTES);
+          const uint32_t sa_lo = sa_hi + C::STRIP_PAD;
           const uint32_t sb_hi = smem_u32(b_ring + sb * C::B_SLOT);
           const uint32_t sb_lo = sb_hi + C::B_TILE_PAD;
           if (leader) {
-          if constexpr (F8) {
-            // e4m3 planes: 32-byte rows (one K = 32 instruction per plane pair), 8-row groups of 256 B = the 32-byte
-            // swizzle repeat, so the dy row advance (8 pixels x 32 B) keeps the canonical K-major layout as well
-            constexpr uint32_t idesc8 = (1u << 4) | (static_cast<uint32_t>(COUT >> 3) << 17) |
-                                        (static_cast<uint32_t>((2 * TILE_M) >> 4) << 24);  // D f32, A / B e4m3
-            const uint32_t sa_l8 = sa_lo + C::STRIP8_PAD;   // sa_lo = a8
-            const uint32_t sb_lw8 = sb_lo + C::B8_TILE_PAD;  // sb_lo = w8
-            umma_f8_pair(d_tmem, umma_smem_desc(sa_l8, BK), umma_smem_desc(sb_lo, BK), idesc8, (kc | tap) != 0 ? 1u : 0u);
-            umma_f8_pair(d_tmem, umma_smem_desc(sa_lo, BK), umma_smem_desc(sb_lw8, BK), idesc8, 1u);
-#pragma unroll
-            for (int k = 0; k < C::KSTEPS; ++k)
-              umma_f16_pair(d_tmem, umma_smem_desc(sa_hi + k * 32, C::ROW_BYTES), umma_smem_desc(sb_hi + k * 32, C::ROW_BYTES),
-                            idesc, 1u);
-          } else {
+          {
 #ifdef DD_PROBES  // timing probes of DESIGN.md §8 / profiles/README.md (build with -DDD_PROBES); results are garbage
           if (p.fp8_probe == 3 || p.fp8_probe == 1) {
             // 3: the intrinsic rate of kind::f8f6f4 — three K = 32 e4m3 MMAs per (chunk, tap) stage and nothing else;
@@ -468,7 +513,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             }
           }
         }
-        if constexpr ((EPI == EPI_F32_STATS || EPI == EPI_F32) && C::CH == 32) {
+        if constexpr ((EPI == EPI_F32_STATS || EPI == EPI_F32) && C::CH == 32 && !F8) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) T[lane * 32 + ((j ^ lane) & 31)] = v[j];
           __syncwarp();

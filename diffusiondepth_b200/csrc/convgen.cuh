@@ -15,7 +15,7 @@ namespace dd {
 struct GenConvArgs {
   int B, H, W;
   int tiles_x, tiles_y, m_tiles, n_tiles;
-  int kc0, kc1;       // 32-channel chunks taken from source 0, then source 1
+  int kc0, kc1;       // GEN_BK-channel chunks taken from source 0, then source 1
   int taps;           // 1 (1x1) or 9 (3x3, pad 1)
   int cout;           // total output channels (n_tiles * NT)
   const float* shift; // [cout] bias / folded BN shift
@@ -38,9 +38,15 @@ struct GenConvArgs {
 // CTA) and each stages only HALF of the weight tile (NT / 2 rows).  Per 32-channel stage a single CTA pulls
 // 2 * (128 + NT) * 64 B from L2 for 3 * NT cycles of MMA work = 64 B/clk at NT = 256, above the ~40 B/clk an SM gets from
 // L2 when all 148 stream at once (profiles/README.md round 2); a pair needs 2 * (128 + NT / 2) * 64 B = 42 B/clk.
+// K chunk of the producer convs / GEMMs: 64 channels = 128-byte operand rows (128-byte swizzle).  With 32-channel chunks
+// (64-byte rows) the tensor pipe sat at 13..40 % in every Swin GEMM (ncu, profiles/README.md round 2) at ~1 us per stage
+// whatever the stage's MMA work: each stage is 2 x (128 + NT) separate 64-byte row requests to TMA; 128-byte rows halve
+// the requests and the barrier round trips per byte.
+constexpr int GEN_BK = 64;
+
 template <int NT, bool PAIR = false>
 struct GenCfg {
-  static constexpr int BK = 32;
+  static constexpr int BK = GEN_BK;
   static constexpr int ROW_BYTES = BK * 2;
   static constexpr int A_BYTES = TILE_M * ROW_BYTES;  // 8 KB per plane
   static constexpr int B_ROWS = PAIR ? NT / 2 : NT;   // weight rows this CTA stages
@@ -48,8 +54,9 @@ struct GenCfg {
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
   static constexpr int EPI_WARPS = 8;
   static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;  // per-warp 32x32 fp32 transpose tile (XOR-swizzled)
-  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 512 - XPOSE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static_assert(STAGES >= 2, "stage too large");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + XPOSE_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   static constexpr int TMEM_COLS = 512;
@@ -395,15 +402,15 @@ __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ in, __half* 
   if (ov) atomicOr(status, 1);
 }
 
-// rgb fp32 NCHW [B,3,H,W] -> fp16 hi/lo NHWC planes [B,H,W,32] (channels 3..31 zero): first ResNet conv input
-__global__ void rgb_to_planes32_kernel(const float* __restrict__ rgb, __half* __restrict__ hi, __half* __restrict__ lo,
-                                       int B, int HW, float scale, int* status) {
+// rgb fp32 NCHW [B,3,H,W] -> fp16 hi/lo NHWC planes [B,H,W,GEN_BK] (channels 3.. zero): first ResNet conv input
+__global__ void rgb_to_planes_kernel(const float* __restrict__ rgb, __half* __restrict__ hi, __half* __restrict__ lo,
+                                     int B, int HW, float scale, int* status) {
   const size_t n = static_cast<size_t>(B) * HW;
   bool ov = false;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n * 32;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n * GEN_BK;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i & 31);
-    const size_t px = i >> 5;
+    const int c = static_cast<int>(i % GEN_BK);
+    const size_t px = i / GEN_BK;
     float v = 0.f;
     if (c < 3) {
       const size_t b = px / HW, p = px % HW;

@@ -97,26 +97,26 @@ int make_strip_map(CUtensorMap* m, const __half* base, int B, int H, int W, int 
   if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(strip) failed: " + std::to_string((int)r));
   return DD_OK;
 }
-// e4m3 activation strip (fp8-correction planes): [B][H][W][C] bytes, box = {32, 8, 18, 1}, 32-byte swizzle
+// e4m3 activation strip (fp8-correction planes): [B][H][W][C] bytes, box = {64, 8, 18, 1}: 64-byte rows, 64-byte swizzle
 int make_strip_map8(CUtensorMap* m, const uint8_t* base, int B, int H, int W, int C) {
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t gstr[3] = {(cuuint64_t)C, (cuuint64_t)W * C, (cuuint64_t)H * W * C};
-  cuuint32_t box[4] = {32, dd::HALO_TW, dd::HALO_TH + 2, 1};
+  cuuint32_t box[4] = {64, dd::HALO_TW, dd::HALO_TH + 2, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(e4m3 strip) failed: " + std::to_string((int)r));
   return DD_OK;
 }
-// e4m3 weights: [9][COUT][CIN] bytes; box = {32, rows, 1}, 32-byte swizzle
+// e4m3 weights: [9][COUT][CIN] bytes; box = {64, rows, 1}, 64-byte swizzle
 int make_w_map8(CUtensorMap* m, const uint8_t* base, int cout, int cin, int box_rows) {
   cuuint64_t gdim[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
   cuuint64_t gstr[2] = {(cuuint64_t)cin, (cuuint64_t)cout * cin};
-  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(e4m3 weight) failed: " + std::to_string((int)r));
   return DD_OK;
@@ -146,14 +146,14 @@ int make_w_map(CUtensorMap* m, const __half* base, int cout, int cin, int bk, in
   return DD_OK;
 }
 
-// general conv weights: [taps][COUT][CIN] fp16; box = {32, NT, 1}
+// general conv weights: [taps][COUT][CIN] fp16; box = {GEN_BK, NT, 1}
 int make_wgen_map(CUtensorMap* m, const __half* base, int cout, int cin, int taps, int nt) {
   cuuint64_t gdim[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)taps};
   cuuint64_t gstr[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
-  cuuint32_t box[3] = {32, (cuuint32_t)nt, 1};
+  cuuint32_t box[3] = {dd::GEN_BK, (cuuint32_t)nt, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(dd::GEN_BK), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(gen weight) failed: " + std::to_string((int)r));
   return DD_OK;
@@ -312,12 +312,12 @@ cudaError_t configure_halo_all_epi() {
 }
 cudaError_t configure_halo_kernels() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<256, 256, 32, dd::EPI_SPLIT, true, true>,
+  if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<256, 256, 64, dd::EPI_SPLIT, true, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                dd::HaloCfg<256, 256, 32, true, true>::SMEM_BYTES)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<256, 256, 32, dd::EPI_F32, true, true>,
+                                dd::HaloCfg<256, 256, 64, true, true>::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<256, 256, 64, dd::EPI_F32, true, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                dd::HaloCfg<256, 256, 32, true, true>::SMEM_BYTES)) != cudaSuccess) return e;
+                                dd::HaloCfg<256, 256, 64, true, true>::SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = configure_pair_all_epi<64, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_pair_all_epi<256, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_halo_all_epi<16, 64, 16>()) != cudaSuccess) return e;
@@ -348,7 +348,7 @@ struct ConvLayer {
   __half* w_swap = nullptr;  // [9][128][CIN]: rows co = hi, 64+co = lo (swapped-operand kernel, narrow layers)
   CUtensorMap mw_swap;
   uint8_t *w8 = nullptr, *lw8 = nullptr;  // e4m3 correction planes [9][COUT][CIN] (DD_FLAG_FP8_CORR, 256 -> 256 layers)
-  CUtensorMap m8_w, m8_lw;                // box {32, COUT / 2, 1} bytes for the CTA-pair kernel
+  CUtensorMap m8_hi, m8_w, m8_lw;         // 64-channel boxes of COUT / 2 rows (fp16 hi plane, e4m3 planes): CTA-pair fp8 kernel
 };
 
 struct Raw {
@@ -605,8 +605,8 @@ size_t carve(dd_engine* e, void* base) {
     ResNetW* rv = &v->rn;
     const size_t pin = static_cast<size_t>(g.B) * rc.H * rc.W;
     const size_t p0 = static_cast<size_t>(g.B) * rc.Hs[0] * rc.Ws[0] * 64;  // largest stage tensor (elements)
-    rv->IN.hi = c.take<__half>(pin * 32);
-    rv->IN.lo = c.take<__half>(pin * 32);
+    rv->IN.hi = c.take<__half>(pin * dd::GEN_BK);
+    rv->IN.lo = c.take<__half>(pin * dd::GEN_BK);
     rv->T.hi = c.take<__half>(p0);
     rv->T.lo = c.take<__half>(p0);
     for (int k = 0; k < 2; ++k) {
@@ -741,12 +741,13 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
     if ((f8 & kF8Out) && epi != dd::EPI_SPLIT) return fail(DD_ERR_INVALID, "fp8 output planes need the split epilogue");
     if (f8 & kF8In) {
       const uint8_t* a8 = reinterpret_cast<const uint8_t*>(in_lo);
-      CUtensorMap m_a8, m_l8;
+      CUtensorMap m_hi64, m_a8, m_l8;
+      if ((rc = make_strip_map(&m_hi64, in_hi, g.B, g.h, g.w, s.cin, 64))) return rc;
       if ((rc = make_strip_map8(&m_a8, a8, g.B, g.h, g.w, s.cin))) return rc;
       if ((rc = make_strip_map8(&m_l8, a8 + static_cast<size_t>(g.B) * g.P * s.cin, g.B, g.h, g.w, s.cin))) return rc;
       err = (epi == dd::EPI_SPLIT)
-                ? launch_pair<256, 256, 32, dd::EPI_SPLIT, true>(ma_hi, m_a8, L.mp_hi, L.m8_w, a, e->sm_count, st, &m_l8, &L.m8_lw)
-                : launch_pair<256, 256, 32, dd::EPI_F32, true>(ma_hi, m_a8, L.mp_hi, L.m8_w, a, e->sm_count, st, &m_l8, &L.m8_lw);
+                ? launch_pair<256, 256, 64, dd::EPI_SPLIT, true>(m_hi64, m_a8, L.m8_hi, L.m8_w, a, e->sm_count, st, &m_l8, &L.m8_lw)
+                : launch_pair<256, 256, 64, dd::EPI_F32, true>(m_hi64, m_a8, L.m8_hi, L.m8_w, a, e->sm_count, st, &m_l8, &L.m8_lw);
     } else if (use_pair) {
 #define PAIR_CASE(ID, CI, CO, BK)                                                                                   \
   case ID:                                                                                                          \
@@ -1021,6 +1022,7 @@ int pack_layer(dd_engine* e, ConvLayer& L, const float* w, const float* b, int c
     if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.lw8), n))) return rc;
     dd::pack_conv_weight8_kernel<<<128, 256, 0, st>>>(w, L.w8, L.lw8, cout, cin, scale);
     CUDA_TRY(cudaGetLastError());
+    if ((rc = make_w_map(&L.m8_hi, L.w_hi, cout, cin, 64, cout / 2))) return rc;
     if ((rc = make_w_map8(&L.m8_w, L.w8, cout, cin, cout / 2))) return rc;
     if ((rc = make_w_map8(&L.m8_lw, L.lw8, cout, cin, cout / 2))) return rc;
   }
@@ -1087,7 +1089,7 @@ int pack_gen(dd_engine* e, GenLayer& L, const std::string& wkey, const std::stri
   L.shuffle = transposed ? 1 : 0;
   L.relu = 1;
   L.nt = (L.cout % 256 == 0) ? 256 : (L.cout % 192 == 0 ? 192 : (L.cout % 128 == 0 ? 128 : 64));
-  if (L.cout % L.nt != 0 || cp % 32 != 0) return fail(DD_ERR_UNSUPPORTED, "producer conv channels not tileable: " + wkey);
+  if (L.cout % L.nt != 0 || cp % dd::GEN_BK != 0) return fail(DD_ERR_UNSUPPORTED, "producer conv channels not tileable: " + wkey);
   const size_t n = static_cast<size_t>(L.cout) * cp * L.taps;
   float *d_scale = nullptr;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_hi), n * 2))) return rc;
@@ -1198,8 +1200,8 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   a.tiles_y = (H + dd::TILE_H - 1) / dd::TILE_H;
   a.m_tiles = a.tiles_x * a.tiles_y * B;
   a.n_tiles = L.cout / L.nt;
-  a.kc0 = c0 / 32;
-  a.kc1 = c1 / 32;
+  a.kc0 = c0 / dd::GEN_BK;
+  a.kc1 = c1 / dd::GEN_BK;
   a.taps = L.taps;
   a.cout = L.cout;
   a.shift = L.shift;
@@ -1219,15 +1221,15 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   CUtensorMap m0h, m0l, m1h, m1l;
   int rc;
   if (L.stride == 1) {
-    if ((rc = make_act_map(&m0h, a0.hi, B, H, W, c0, 32))) return rc;
-    if ((rc = make_act_map(&m0l, a0.lo, B, H, W, c0, 32))) return rc;
+    if ((rc = make_act_map(&m0h, a0.hi, B, H, W, c0, dd::GEN_BK))) return rc;
+    if ((rc = make_act_map(&m0l, a0.lo, B, H, W, c0, dd::GEN_BK))) return rc;
   } else {
-    if ((rc = make_act_map_strided(&m0h, a0.hi, B, src_h, src_w, c0, 32, L.stride))) return rc;
-    if ((rc = make_act_map_strided(&m0l, a0.lo, B, src_h, src_w, c0, 32, L.stride))) return rc;
+    if ((rc = make_act_map_strided(&m0h, a0.hi, B, src_h, src_w, c0, dd::GEN_BK, L.stride))) return rc;
+    if ((rc = make_act_map_strided(&m0l, a0.lo, B, src_h, src_w, c0, dd::GEN_BK, L.stride))) return rc;
   }
   if (c1 > 0) {
-    if ((rc = make_act_map(&m1h, a1.hi, B, H, W, c1, 32))) return rc;
-    if ((rc = make_act_map(&m1l, a1.lo, B, H, W, c1, 32))) return rc;
+    if ((rc = make_act_map(&m1h, a1.hi, B, H, W, c1, dd::GEN_BK))) return rc;
+    if ((rc = make_act_map(&m1l, a1.lo, B, H, W, c1, dd::GEN_BK))) return rc;
   } else {
     m1h = m0h;
     m1l = m0l;
@@ -1255,7 +1257,7 @@ int pack_resnet(dd_engine* e, cudaStream_t st, float* scratch) {
       ResBlockW& W = r.blocks[s][b];
       const std::string bp = "backbone.layers." + std::to_string(s) + "." + std::to_string(b) + ".";
       const int cin = b == 0 ? cprev : r.C[s];
-      const int pad = (cin % 32) ? 32 : 0;
+      const int pad = (cin % dd::GEN_BK) ? dd::GEN_BK : 0;
       if ((rc = pack_gen(e, W.c1, bp + "conv1.weight", bp + "bn1", cin, r.C[s], 9, false, st, scratch, pad))) return rc;
       W.c1.stride = b == 0 ? 2 : 1;
       if ((rc = pack_gen(e, W.c2, bp + "conv2.weight", bp + "bn2", r.C[s], r.C[s], 9, false, st, scratch))) return rc;
@@ -1277,17 +1279,17 @@ int run_resnet(dd_engine* e, const float* rgb, float* const* feats_out, cudaStre
   ResNetW& r = e->rn;
   const int B = e->cfg.batch;
   {
-    const size_t n = static_cast<size_t>(B) * r.H * r.W * 32;
+    const size_t n = static_cast<size_t>(B) * r.H * r.W * dd::GEN_BK;
     int blocks = static_cast<int>((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    dd::rgb_to_planes32_kernel<<<blocks, 256, 0, st>>>(rgb, r.IN.hi, r.IN.lo, B, r.H * r.W, kProdScale, e->status);
+    dd::rgb_to_planes_kernel<<<blocks, 256, 0, st>>>(rgb, r.IN.hi, r.IN.lo, B, r.H * r.W, kProdScale, e->status);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
   }
   const Planes none;
   int rc;
   Planes src = r.IN;
-  int src_c = 32, src_h = r.H, src_w = r.W;
+  int src_c = dd::GEN_BK, src_h = r.H, src_w = r.W;
   for (int s = 0; s < 4; ++s) {
     const int C = r.C[s], H = r.Hs[s], W = r.Ws[s];
     int cur = 0;
@@ -1344,7 +1346,7 @@ int pack_gemm(dd_engine* e, Gemm& G, const std::string& wkey, const std::string&
   G.K = K;
   G.N = N;
   G.nt = (N % 256 == 0) ? 256 : 192;
-  if (N % G.nt != 0 || K % 32 != 0) return fail(DD_ERR_UNSUPPORTED, "linear layer not tileable: " + wkey);
+  if (N % G.nt != 0 || K % dd::GEN_BK != 0) return fail(DD_ERR_UNSUPPORTED, "linear layer not tileable: " + wkey);
   const size_t n = static_cast<size_t>(N) * K;
   int rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&G.w_hi), n * 2))) return rc;
@@ -1440,7 +1442,7 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   const CUtensorMap& mbh = pair ? ((nt == G.nt) ? G.mp_hi : G.mp_hi_alt) : ((nt == G.nt) ? G.mb_hi : G.mb_hi_alt);
   const CUtensorMap& mbl = pair ? ((nt == G.nt) ? G.mp_lo : G.mp_lo_alt) : ((nt == G.nt) ? G.mb_lo : G.mb_lo_alt);
   a.n_tiles = G.N / nt;
-  a.kc0 = G.K / 32;
+  a.kc0 = G.K / dd::GEN_BK;
   a.kc1 = 0;
   a.taps = 1;
   a.cout = G.N;
@@ -1459,8 +1461,8 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   a.status = e->status;
   CUtensorMap mh, ml;
   int rc;
-  if ((rc = make_act_map(&mh, A.hi, 1, a.H, 16, G.K, 32))) return rc;
-  if ((rc = make_act_map(&ml, A.lo, 1, a.H, 16, G.K, 32))) return rc;
+  if ((rc = make_act_map(&mh, A.hi, 1, a.H, 16, G.K, dd::GEN_BK))) return rc;
+  if ((rc = make_act_map(&ml, A.lo, 1, a.H, 16, G.K, dd::GEN_BK))) return rc;
   const int grid = gen_grid(e, pair, a.m_tiles, a.n_tiles);
   const cudaError_t err = launch_gen_nt(nt, pair, grid, st, mh, ml, mh, ml, mbh, mbl, a);
   e->launches++;
@@ -1904,7 +1906,7 @@ int dd_enable_producers(dd_handle h, const dd_producer_config* pc) {
     p.C[i] = pc->channels[i];
     p.H[i] = pc->heights[i];
     p.W[i] = pc->widths[i];
-    if (p.C[i] % 32 != 0 || p.C[i] <= 0) return fail(DD_ERR_UNSUPPORTED, "feature channels must be multiples of 32");
+    if (p.C[i] % dd::GEN_BK != 0 || p.C[i] <= 0) return fail(DD_ERR_UNSUPPORTED, "feature channels must be multiples of 64");
     if (p.neck && p.C[i] % 192 != 0) return fail(DD_ERR_UNSUPPORTED, "neck channel counts must tile by 192");
     // the FPN's adaptive_avg_pool2d (reference head :121) is the identity only for exact 2x pyramids; otherwise the
     // ConvT output (2x the coarser level) is average-pooled down to the lateral's size by a dedicated kernel
@@ -2085,7 +2087,7 @@ int dd_run_backbone(dd_handle h, const float* rgb, float* const* feats_out, void
 // Debug / tuning aid: time the GEMM-mode kernel on synthetic planes.  mode: 0 fp32 out, 1 fp32 out + residual add,
 // 2 GELU -> planes, 3 no output at all (mainloop + TMEM drain only).
 int dd_bench_gemm(dd_handle h, int32_t M, int32_t K, int32_t N, int32_t mode, int32_t iters, float* ms_out) {
-  if (!h || !ms_out || M < 1 || K % 32 || N % 192 && N % 256) return fail(DD_ERR_INVALID, "bad argument");
+  if (!h || !ms_out || M < 1 || K % dd::GEN_BK || N % 192 && N % 256) return fail(DD_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->cap_stream;
   const size_t Mp = (static_cast<size_t>(M) + 127) / 128 * 128 + 128;
@@ -2302,13 +2304,13 @@ int dd_conv3x3(dd_handle h, const float* x, const float* w, const float* b, floa
     a.tiles_y = (height + dd::HALO_TH - 1) / dd::HALO_TH;
     a.num_tiles = a.tiles_x * a.tiles_y * batch;
     CUtensorMap ma_hi, m_a8, m_l8, mb_hi, m_w8, m_lw8;
-    if ((rc = make_strip_map(&ma_hi, hi, batch, height, width, cin, 32))) return rc;
+    if ((rc = make_strip_map(&ma_hi, hi, batch, height, width, cin, 64))) return rc;
     if ((rc = make_strip_map8(&m_a8, a8, batch, height, width, cin))) return rc;
     if ((rc = make_strip_map8(&m_l8, l8, batch, height, width, cin))) return rc;
-    if ((rc = make_w_map(&mb_hi, whi, cout, cin, 32, cout / 2))) return rc;
+    if ((rc = make_w_map(&mb_hi, whi, cout, cin, 64, cout / 2))) return rc;
     if ((rc = make_w_map8(&m_w8, w8, cout, cin, cout / 2))) return rc;
     if ((rc = make_w_map8(&m_lw8, lw8, cout, cin, cout / 2))) return rc;
-    err = launch_pair<256, 256, 32, dd::EPI_F32, true>(ma_hi, m_a8, mb_hi, m_w8, a, h->sm_count, st, &m_l8, &m_lw8);
+    err = launch_pair<256, 256, 64, dd::EPI_F32, true>(ma_hi, m_a8, mb_hi, m_w8, a, h->sm_count, st, &m_l8, &m_lw8);
   } else if (h->cfg.flags & DD_FLAG_HALO_CONV) {
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     const int hbk = kHaloBK[sid];
