@@ -52,8 +52,9 @@ struct GenCfg {
   static constexpr int B_ROWS = PAIR ? NT / 2 : NT;   // weight rows this CTA stages
   static constexpr int B_BYTES = B_ROWS * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-  static constexpr int EPI_WARPS = 8;
-  static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 32 * 4;  // per-warp 32x32 fp32 transpose tile (XOR-swizzled)
+  static constexpr int EPI_WARPS = 16;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;         // 4 role warps + the epilogue warps
+  static constexpr int XPOSE_BYTES = EPI_WARPS * 32 * 16 * 4;  // per-warp [32][16] fp32 re-distribution tile (XOR-swizzled)
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 512 - XPOSE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static_assert(STAGES >= 2, "stage too large");
@@ -65,7 +66,7 @@ struct GenCfg {
 
 // PAIR: launched as clusters of 2; work item = (pair of M tiles, N tile); tmB_* then have a box of NT / 2 rows.
 template <int NT, bool PAIR = false>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__((GenCfg<NT, PAIR>::THREADS), 1)
 convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_constant__ CUtensorMap tmA0_lo,
                     const __grid_constant__ CUtensorMap tmA1_hi, const __grid_constant__ CUtensorMap tmA1_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -105,7 +106,7 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], PAIR ? 16 : 8);  // eight epilogue warps (of both CTAs, on the leader's barrier)
+      mbar_init(&tempty_bar[b], (PAIR ? 2 : 1) * C::EPI_WARPS);  // the epilogue warps (of both CTAs, on the leader's barrier)
     }
     fence_barrier_init();
   }
@@ -237,21 +238,23 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
       buf ^= 1;
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- epilogue: 8 warps = 2 groups x 128 TMEM lanes;
-    // group g drains the 32-column chunks with index % 2 == g.  tcgen05.ld hands each thread one ROW (pixel/token) of
-    // the chunk; a per-warp XOR-swizzled 32x32 shared-memory tile turns that into one COLUMN per lane, so every global
-    // access below is a fully coalesced 128-byte row segment (row-per-thread stores were the bottleneck of short-K GEMMs:
-    // 32 partial lines per instruction).
+    // ---------------------------------------------------------------- epilogue: 16 warps = 4 groups x 128 TMEM lanes;
+    // group g drains the 16-column chunks with index % 4 == g.  (ncu, round 2: with 8 warps on 32-column chunks the
+    // GELU -> planes epilogue of every FFN1 ran at 2 warps per scheduler, 42 % issue-active, and took twice the mainloop:
+    // 16 warps at half the registers each.)  tcgen05.ld hands each thread one ROW (pixel / token) of the chunk.
+    //   fp32-only outputs: a per-warp XOR-swizzled [32][16] shared-memory tile re-distributes the chunk so that a lane
+    //     holds one float4 of a row and 4 lanes cover the row's 64 bytes: every global access is a full 64-byte segment;
+    //   plane outputs (fp16 hi / lo for the next GEMM): row-per-thread, 32 contiguous bytes per row and plane.
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
     const int m = q * 32 + lane;
     const int r = m >> 4, c = m & 15;
-    float* T = xpose + (warp - 4) * 1024;
+    float* T = xpose + (warp - 4) * (32 * 16);
     uint32_t full_phase = 0;
     int buf = 0;
     bool overflow = false;
     const int cq = p.cout >> 2;
-    constexpr int NCH = NT / 32;
+    constexpr int NCH = NT / 16;
     for (int work = work0; work < num_work; work += work_step) {
       const int nt = work % p.n_tiles;
       const int mt = (PAIR ? 2 * (work / p.n_tiles) + static_cast<int>(rank) : work / p.n_tiles);
@@ -265,11 +268,11 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
       full_phase ^= (1u << buf);
       tc_fence_after();
       const bool xpose_path = (p.out_hi == nullptr);  // fp32-only traffic: coalesce through the transpose tile
-      for (int ci = grp; ci < NCH; ci += 2) {
-        const int ch0 = ci * 32;
+      for (int ci = grp; ci < NCH; ci += 4) {
+        const int ch0 = ci * 16;
         const int n0 = nt * NT + ch0;
-        uint32_t rr[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * NT + ch0), rr);
+        uint32_t rr[16];
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * NT + ch0), rr);
         tmem_ld_wait();
         uint32_t o_lane;
         if (p.shuffle) {
@@ -280,68 +283,83 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           o_lane = row_base + static_cast<uint32_t>(n0);
         }
         if (xpose_path) {
+          // row `lane`, float4 slot s -> T[lane][s ^ ((lane >> 1) & 3)]: conflict-free 16-byte writes and reads
 #pragma unroll
-          for (int j = 0; j < 32; ++j) T[lane * 32 + ((j ^ lane) & 31)] = __uint_as_float(rr[j]);
+          for (int sl = 0; sl < 4; ++sl)
+            *reinterpret_cast<float4*>(T + lane * 16 + ((sl ^ ((lane >> 1) & 3)) << 2)) =
+                make_float4(__uint_as_float(rr[4 * sl]), __uint_as_float(rr[4 * sl + 1]), __uint_as_float(rr[4 * sl + 2]),
+                            __uint_as_float(rr[4 * sl + 3]));
           __syncwarp();
-          const float sh = __ldg(p.shift + n0 + lane);
+          const int sl = lane & 3;  // this lane's float4 slot: channels n0 + 4 sl .. + 3
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0) + sl);
+          uint32_t o[4];
+          float4 ad[4];
 #pragma unroll
-          for (int r0 = 0; r0 < 32; r0 += 8) {
-            uint32_t o[8];
-            float ad[8];
+          for (int k = 0; k < 4; ++k) {  // rows (lane >> 2) + 8 k: issue the addend loads before any store
+            const int row = (lane >> 2) + 8 * k;
+            o[k] = __shfl_sync(0xffffffffu, o_lane, row) + 4 * sl;
+            ad[k] = (p.add32 && ((vmask >> row) & 1u)) ? __ldg(reinterpret_cast<const float4*>(p.add32 + o[k]))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {  // issue the (coalesced) addend loads of 8 rows before any store
-              o[k] = __shfl_sync(0xffffffffu, o_lane, r0 + k) + lane;
-              ad[k] = (p.add32 && ((vmask >> (r0 + k)) & 1u)) ? __ldg(p.add32 + o[k]) : 0.f;
+          for (int k = 0; k < 4; ++k) {
+            const int row = (lane >> 2) + 8 * k;
+            if (!((vmask >> row) & 1u)) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(T + row * 16 + ((sl ^ ((row >> 1) & 3)) << 2));
+            float t[4] = {fmaf(a4.x, p.acc_scale, sh.x), fmaf(a4.y, p.acc_scale, sh.y), fmaf(a4.z, p.acc_scale, sh.z),
+                          fmaf(a4.w, p.acc_scale, sh.w)};
+            const float av[4] = {ad[k].x, ad[k].y, ad[k].z, ad[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (p.add_first) t[j] += av[j];
+              if (p.relu == 1) t[j] = fmaxf(t[j], 0.f);
+              else if (p.relu == 2) t[j] = 0.5f * t[j] * (1.f + erff(t[j] * 0.70710678118654752f));
+              if (!p.add_first) t[j] += av[j];
             }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if (!((vmask >> (r0 + k)) & 1u)) continue;  // warp-uniform
-              float t = fmaf(T[(r0 + k) * 32 + ((lane ^ (r0 + k)) & 31)], p.acc_scale, sh);
-              if (p.add_first) t += ad[k];
-              if (p.relu == 1) t = fmaxf(t, 0.f);
-              else if (p.relu == 2) t = 0.5f * t * (1.f + erff(t * 0.70710678118654752f));
-              if (!p.add_first) t += ad[k];
-              if (p.y32) p.y32[o[k]] = t;
-            }
+            if (p.y32) *reinterpret_cast<float4*>(p.y32 + o[k]) = make_float4(t[0], t[1], t[2], t[3]);
           }
           __syncwarp();
         } else if (valid) {
-          // row-per-thread path (fp16 plane outputs: 64 contiguous bytes per row and plane)
-          float v[32];
+          // row-per-thread path (fp16 plane outputs: 32 contiguous bytes per row and plane)
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rr[j]), p.acc_scale, __ldg(p.shift + n0 + j));
-          float ad[32];
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0) + j4);
+            v[4 * j4] = fmaf(__uint_as_float(rr[4 * j4]), p.acc_scale, sh.x);
+            v[4 * j4 + 1] = fmaf(__uint_as_float(rr[4 * j4 + 1]), p.acc_scale, sh.y);
+            v[4 * j4 + 2] = fmaf(__uint_as_float(rr[4 * j4 + 2]), p.acc_scale, sh.z);
+            v[4 * j4 + 3] = fmaf(__uint_as_float(rr[4 * j4 + 3]), p.acc_scale, sh.w);
+          }
+          if (p.add32 && p.add_first) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) ad[j] = 0.f;
-          if (p.add32) {
-            const float4* a4 = reinterpret_cast<const float4*>(p.add32 + o_lane);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldg(a4 + j);
-              ad[4 * j] = t.x;
-              ad[4 * j + 1] = t.y;
-              ad[4 * j + 2] = t.z;
-              ad[4 * j + 3] = t.w;
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.add32 + o_lane) + j4);
+              v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
             }
           }
+          if (p.relu == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float t = v[j];
-            if (p.add_first) t += ad[j];
-            if (p.relu == 1) t = fmaxf(t, 0.f);
-            else if (p.relu == 2) t = 0.5f * t * (1.f + erff(t * 0.70710678118654752f));
-            if (!p.add_first) t += ad[j];
-            v[j] = t;
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.relu == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+          }
+          if (p.add32 && !p.add_first) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.add32 + o_lane) + j4);
+              v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+            }
           }
           if (p.y32) {
             float4* d4 = reinterpret_cast<float4*>(p.y32 + o_lane);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          __align__(16) __half hi[32];
-          __align__(16) __half lo[32];
+          __align__(16) __half hi[16];
+          __align__(16) __half lo[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             const float sc = v[j] * p.split_scale;
             overflow |= (fabsf(sc) > 60000.f);
             hi[j] = __float2half_rn(sc);
@@ -350,7 +368,7 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o_lane);
           uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o_lane);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             dh[j] = reinterpret_cast<const uint4*>(hi)[j];
             dl[j] = reinterpret_cast<const uint4*>(lo)[j];
           }

@@ -1150,12 +1150,12 @@ template <int NT, bool PAIR>
 cudaError_t launch_gen(int grid, cudaStream_t st, const CUtensorMap& m0h, const CUtensorMap& m0l, const CUtensorMap& m1h,
                        const CUtensorMap& m1l, const CUtensorMap& bh, const CUtensorMap& bl, const dd::GenConvArgs& a) {
   if constexpr (!PAIR) {
-    dd::convgen_umma_kernel<NT, false><<<grid, 384, dd::GenCfg<NT, false>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, bh, bl, a);
+    dd::convgen_umma_kernel<NT, false><<<grid, dd::GenCfg<NT, false>::THREADS, dd::GenCfg<NT, false>::SMEM_BYTES, st>>>(m0h, m0l, m1h, m1l, bh, bl, a);
     return cudaGetLastError();
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(384);
+    cfg.blockDim = dim3(dd::GenCfg<NT, true>::THREADS);
     cfg.dynamicSmemBytes = dd::GenCfg<NT, true>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute at[1];

@@ -25,6 +25,8 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 rgb, gt, noise = s["rgb"].contiguous(), s["gt"].contiguous(), s["noise"]
 t_bb = timeit(lambda: eng.run_backbone(rgb))
+feats = eng.run_backbone(rgb, want_feats=True)
+t_cond_alone = timeit(lambda: eng.build_condition(feats))  # includes 4 NCHW -> plane transposes, runs the graph
 def cond_only():
     eng.run_backbone(rgb); eng.build_condition(None)
 t_bc = timeit(cond_only)
@@ -33,5 +35,5 @@ def upto_loop():
 t_all = timeit(upto_loop)
 with torch.no_grad():
     t_fwd = timeit(lambda: m(s))
-print(f"[{os.environ.get('AB_TAG','')}] backbone {t_bb:.2f} ms | neck+FPN {t_bc - t_bb:.2f} ms | encoder+loop+decoder {t_all - t_bc:.2f} ms "
+print(f"[{os.environ.get('AB_TAG','')}] backbone {t_bb:.2f} ms | neck+FPN {t_bc - t_bb:.2f} ms (alone, from NCHW feats: {t_cond_alone:.2f} ms) | encoder+loop+decoder {t_all - t_bc:.2f} ms "
       f"({(t_all - t_bc) / T:.3f} ms/step) | engine calls {t_all:.2f} ms | plugin forward {t_fwd:.2f} ms ({4e3 / t_fwd:.1f} maps/s)", flush=True)
