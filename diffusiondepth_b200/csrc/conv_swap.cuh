@@ -25,10 +25,17 @@ constexpr int SWAP_TH = 16;  // pixel tile 16 x 16 = 256 = UMMA N
 constexpr int SWAP_TW = 16;
 constexpr int SWAP_N = 256;
 
-template <int CIN, int COUT, int BK>
+// HALO = true: ROW-HALO REUSE of the pixel operand, as in conv_halo.cuh.  ncu (round 1 / 2): the plain kernel re-fetches the
+// 256-pixel patch for each of the 9 taps and sits on the L2 -> SM feed (lts 54 %, 80 B/clk needed for 512 cycles of MMA
+// work per 32-channel stage against the ~40 B/clk an SM gets) with the tensor pipe at 70 %.  Here a ring UNIT holds, for
+// one 32-channel chunk and one dx, the [18 rows][16 cols] column-shifted strip of both planes (36 KB); tap (dy, dx) is
+// that strip advanced dy rows = 16 pixels x 64 B = two 64-byte-swizzle repeats, so the canonical K-major B descriptor
+// still addresses it.  Pixel traffic 9 x 256 -> 3 x 288 rows per chunk; weights get their own ring (8 KB per tap).
+template <int CIN, int COUT, int BK, bool HALO = false>
 struct SwapCfg {
   static_assert(COUT == 64 || COUT == 16, "swap kernel serves the narrow layers");
   static_assert(CIN % BK == 0 && (BK == 16 || BK == 32), "bad K chunk");
+  static_assert(!HALO || BK == 32, "halo variant: 64-byte rows");
   static constexpr int KC = CIN / BK;
   static constexpr int K_ITERS = 9 * KC;
   static constexpr int ROW_BYTES = BK * 2;
@@ -39,25 +46,38 @@ struct SwapCfg {
   static constexpr int STAGES_RAW = (220 * 1024 - XCH_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static_assert(STAGES >= 2, "stage too large");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + XCH_BYTES;
+  // halo variant: strip units + weight slots
+  static constexpr int STRIP_BYTES = (SWAP_TH + 2) * SWAP_TW * ROW_BYTES;  // one plane of one dx: 18 x 16 pixel rows
+  static constexpr int UNIT_BYTES = 2 * STRIP_BYTES;                       // hi, lo
+  static constexpr int UNITS = 4;
+  static constexpr int W_SLOTS = 6;
+  static_assert(STRIP_BYTES % 1024 == 0 && W_BYTES % 1024 == 0, "operand tiles stay 1024-byte aligned");
+  static constexpr int RING_BYTES = HALO ? UNITS * UNIT_BYTES + W_SLOTS * W_BYTES : STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 + 512 + XCH_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit");
   static constexpr int TMEM_COLS = 512;                  // 2 accumulator buffers x 256 pixel columns
   static constexpr int GROUP_CH = COUT / 4;
 };
 
-template <int CIN, int COUT, int BK, int EPI>
+// HALO: tmP_* are strip maps (box {BK, 16, 18, 1}); barrier arrays: full / empty [0 .. UNITS) for the strip units, then
+// [8 .. 8 + W_SLOTS) for the weight slots.
+template <int CIN, int COUT, int BK, int EPI, bool HALO = false>
 __global__ void __launch_bounds__(256, 1)
 conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_constant__ CUtensorMap tmP_lo,
                     const __grid_constant__ CUtensorMap tmW, const ConvArgs p) {
-  using C = SwapCfg<CIN, COUT, BK>;
+  using C = SwapCfg<CIN, COUT, BK, HALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ctrl = smem + C::STAGES * C::STAGE_BYTES;
+  uint8_t* ctrl = smem + C::RING_BYTES;
+  constexpr int NBAR = HALO ? 16 : C::STAGES;  // halo: 8 slots reserved for units + 8 for weight slots
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
-  uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* empty_bar = full_bar + NBAR;
+  uint64_t* tfull_bar = empty_bar + NBAR;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* xch = reinterpret_cast<float*>(ctrl + 512);
+  static_assert((2 * NBAR + 4) * 8 + 8 <= 512, "barrier block");
+  static_assert(!HALO || (C::UNITS <= 8 && C::W_SLOTS <= 8), "barrier slots");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,7 +86,7 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
     tma_prefetch_desc(&tmP_hi);
     tma_prefetch_desc(&tmP_lo);
     tma_prefetch_desc(&tmW);
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < NBAR; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -86,7 +106,50 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   auto stage_ptr = [&](int s) { return smem + s * C::STAGE_BYTES; };
 
-  if (warp == 0) {
+  if (HALO && (warp == 0 || warp == 3)) {
+    // ------------------------------------------------------------------ halo variant: warp 0 streams the strip units
+    // (chunk, dx), warp 3 the weight tiles (chunk, dx, dy); whole warp walks, one elected lane issues
+    const bool strips = (warp == 0);
+    const bool leader = elect_one();
+    int slot = 0;
+    uint32_t phase = 0;
+    uint8_t* w_ring = smem + C::UNITS * C::UNIT_BYTES;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * SWAP_TW, y0 = ty * SWAP_TH;
+      for (int kc = 0; kc < C::KC; ++kc) {
+        for (int dx = 0; dx < 3; ++dx) {
+          if (strips) {
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            uint8_t* d = smem + slot * C::UNIT_BYTES;
+            if (leader) {
+              mbar_arrive_expect_tx(&full_bar[slot], C::UNIT_BYTES);
+              tma_load_4d(d, &tmP_hi, &full_bar[slot], kc * BK, x0 + dx - 1, y0 - 1, img);
+              tma_load_4d(d + C::STRIP_BYTES, &tmP_lo, &full_bar[slot], kc * BK, x0 + dx - 1, y0 - 1, img);
+            }
+            __syncwarp();
+            if (++slot == C::UNITS) {
+              slot = 0;
+              phase ^= 1;
+            }
+          } else {
+            for (int dy = 0; dy < 3; ++dy) {
+              mbar_wait(&empty_bar[8 + slot], phase ^ 1);
+              if (leader) {
+                mbar_arrive_expect_tx(&full_bar[8 + slot], C::W_BYTES);
+                tma_load_3d(w_ring + slot * C::W_BYTES, &tmW, &full_bar[8 + slot], kc * BK, 0, dy * 3 + dx);
+              }
+              __syncwarp();
+              if (++slot == C::W_SLOTS) {
+                slot = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (!HALO && warp == 0) {
     // ------------------------------------------------------------------ TMA producer: whole warp walks the loop, one
     // elected lane issues the three copies of a stage back to back (see conv_halo.cuh)
     const bool leader = elect_one();
@@ -121,6 +184,54 @@ conv3x3_swap_kernel(const __grid_constant__ CUtensorMap tmP_hi, const __grid_con
     constexpr uint32_t idesc = umma_idesc_f16(128, SWAP_N);
     int stage = 0, buf = 0;
     uint32_t phase = 0, acc_phase = 0;
+    if constexpr (HALO) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      const uint32_t w_ring = smem_u32(smem + C::UNITS * C::UNIT_BYTES);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * SWAP_N);
+        for (int kc = 0; kc < C::KC; ++kc) {
+          for (int dx = 0; dx < 3; ++dx) {
+            mbar_wait(&full_bar[stage], phase);
+            const uint32_t unit = smem_u32(smem + stage * C::UNIT_BYTES);
+            for (int dy = 0; dy < 3; ++dy) {
+              mbar_wait(&full_bar[8 + ws], wphase);
+              tc_fence_after();
+              const uint32_t sw = w_ring + ws * C::W_BYTES;
+              const uint32_t sp_hi = unit + dy * SWAP_TW * C::ROW_BYTES;  // 16 pixels down = two swizzle repeats
+              const uint32_t sp_lo = sp_hi + C::STRIP_BYTES;
+              if (leader) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint64_t wd = umma_smem_desc(sw + k * 32, C::ROW_BYTES);
+                  umma_f16(d_tmem, wd, umma_smem_desc(sp_lo + k * 32, C::ROW_BYTES), idesc, (kc | dx | dy | k) != 0 ? 1u : 0u);
+                  umma_f16(d_tmem, wd, umma_smem_desc(sp_hi + k * 32, C::ROW_BYTES), idesc, 1u);
+                }
+                umma_commit(&empty_bar[8 + ws]);
+              }
+              __syncwarp();
+              if (++ws == C::W_SLOTS) {
+                ws = 0;
+                wphase ^= 1;
+              }
+            }
+            if (leader) {
+              umma_commit(&empty_bar[stage]);
+              if (kc == C::KC - 1 && dx == 2) umma_commit(&tfull_bar[buf]);
+            }
+            __syncwarp();
+            if (++stage == C::UNITS) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        acc_phase ^= (1u << buf);
+        buf ^= 1;
+      }
+    } else
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[buf], ((acc_phase >> buf) & 1u) ^ 1u);
       tc_fence_after();

@@ -133,6 +133,18 @@ int make_patch_map(CUtensorMap* m, const __half* base, int B, int H, int W, int 
   if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(patch) failed: " + std::to_string((int)r));
   return DD_OK;
 }
+// column-shifted strip for the row-halo variant of the swapped-operand kernel: box = {bk, 16, 18, 1}
+int make_swap_strip_map(CUtensorMap* m, const __half* base, int B, int H, int W, int C, int bk) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, dd::SWAP_TW, dd::SWAP_TH + 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DD_ERR_CUDA, "cuTensorMapEncodeTiled(swap strip) failed: " + std::to_string((int)r));
+  return DD_OK;
+}
 // weights: [9][COUT][CIN] fp16; box = {bk, COUT, 1}
 int make_w_map(CUtensorMap* m, const __half* base, int cout, int cin, int bk, int box_rows = 0) {
   cuuint64_t gdim[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
@@ -234,28 +246,30 @@ constexpr bool kUseHalo[5] = {true, true, true, false, false};
 // traffic through shared memory, and since the TMA producers issue from an elected lane of a whole warp the two CTAs'
 // copies no longer trail the MMAs).  Round 1 had measured the 256->256 pair as equal: that was with lone-lane producers.
 constexpr bool kUsePair[5] = {false, true, true, false, false};
-template <int CIN, int COUT, int BK, int EPI>
+template <int CIN, int COUT, int BK, int EPI, bool HALO = false>
 cudaError_t launch_swap(const CUtensorMap& p_hi, const CUtensorMap& p_lo, const CUtensorMap& w, const dd::ConvArgs& args,
                         int sm_count, cudaStream_t st) {
-  using C = dd::SwapCfg<CIN, COUT, BK>;
+  using C = dd::SwapCfg<CIN, COUT, BK, HALO>;
   int grid = args.num_tiles < sm_count ? args.num_tiles : sm_count;
-  dd::conv3x3_swap_kernel<CIN, COUT, BK, EPI><<<grid, 256, C::SMEM_BYTES, st>>>(p_hi, p_lo, w, args);
+  dd::conv3x3_swap_kernel<CIN, COUT, BK, EPI, HALO><<<grid, 256, C::SMEM_BYTES, st>>>(p_hi, p_lo, w, args);
   return cudaGetLastError();
 }
-template <int CIN, int COUT, int BK>
+template <int CIN, int COUT, int BK, bool HALO = false>
 cudaError_t configure_swap() {
-  using C = dd::SwapCfg<CIN, COUT, BK>;
-  cudaError_t e = cudaFuncSetAttribute(dd::conv3x3_swap_kernel<CIN, COUT, BK, dd::EPI_F32_STATS>,
+  using C = dd::SwapCfg<CIN, COUT, BK, HALO>;
+  cudaError_t e = cudaFuncSetAttribute(dd::conv3x3_swap_kernel<CIN, COUT, BK, dd::EPI_F32_STATS, HALO>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dd::conv3x3_swap_kernel<CIN, COUT, BK, dd::EPI_F32>,
+  return cudaFuncSetAttribute(dd::conv3x3_swap_kernel<CIN, COUT, BK, dd::EPI_F32, HALO>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
 }
 cudaError_t configure_swap_kernels() {
   cudaError_t e;
   if ((e = configure_swap<16, 64, 16>()) != cudaSuccess) return e;
   if ((e = configure_swap<256, 64, 32>()) != cudaSuccess) return e;
-  return configure_swap<64, 16, 32>();
+  if ((e = configure_swap<64, 16, 32>()) != cudaSuccess) return e;
+  if ((e = configure_swap<256, 64, 32, true>()) != cudaSuccess) return e;
+  return configure_swap<64, 16, 32, true>();
 }
 template <int CIN, int COUT, int BK, int EPI>
 cudaError_t launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
@@ -437,6 +451,7 @@ struct dd_engine {
   // (profiles/README.md); a product build ignores the variables altogether
   int probe_fp8 = 0, swap_mask = -1, halo_mask = -1, pair_mask = -1;
   int genpair_mask = 1;  // DD_GENPAIR=0 (probes build): producer convs / GEMMs on single CTAs
+  int swaphalo_mask = 1; // DD_SWAPHALO=0 (probes build): narrow layers on the plain swapped-operand kernel
   bool want_clk_probe = false;
   bool weights_ready = false;
   std::map<std::string, Raw> raw;
@@ -695,9 +710,25 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
     CUtensorMap mp_hi, mp_lo;
     int rc;
     const int bk = kSwapBK[L.sid];
-    if ((rc = make_patch_map(&mp_hi, in_hi, g.B, g.h, g.w, s.cin, bk))) return rc;
-    if ((rc = make_patch_map(&mp_lo, in_lo, g.B, g.h, g.w, s.cin, bk))) return rc;
+    // row-halo variant (three column-shifted strips per chunk instead of nine shifted patches) for the 32-channel-chunk
+    // layers when the engine runs the halo kernels at all
+    const bool swap_halo = (e->cfg.flags & DD_FLAG_HALO_CONV) && bk == 32 && e->swaphalo_mask != 0;
+    if (swap_halo) {
+      if ((rc = make_swap_strip_map(&mp_hi, in_hi, g.B, g.h, g.w, s.cin, bk))) return rc;
+      if ((rc = make_swap_strip_map(&mp_lo, in_lo, g.B, g.h, g.w, s.cin, bk))) return rc;
+    } else {
+      if ((rc = make_patch_map(&mp_hi, in_hi, g.B, g.h, g.w, s.cin, bk))) return rc;
+      if ((rc = make_patch_map(&mp_lo, in_lo, g.B, g.h, g.w, s.cin, bk))) return rc;
+    }
     const bool st_ = (epi == dd::EPI_F32_STATS);
+    if (swap_halo) {
+      switch (L.sid) {
+        case 3: err = st_ ? launch_swap<256, 64, 32, dd::EPI_F32_STATS, true>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st)
+                          : launch_swap<256, 64, 32, dd::EPI_F32, true>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st); break;
+        case 4: err = st_ ? launch_swap<64, 16, 32, dd::EPI_F32_STATS, true>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st)
+                          : launch_swap<64, 16, 32, dd::EPI_F32, true>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st); break;
+      }
+    } else
     switch (L.sid) {
       case 0: err = st_ ? launch_swap<16, 64, 16, dd::EPI_F32_STATS>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st)
                         : launch_swap<16, 64, 16, dd::EPI_F32>(mp_hi, mp_lo, L.mw_swap, a, e->sm_count, st); break;
@@ -845,8 +876,8 @@ int run_apply(dd_engine* e, int which, const float* temb, int temb_bstride, __ha
   a.status = e->status;
   // the tiled bilinear kernel needs the 32-pixel segment's source span to fit its 18-column staging buffer
   // (and two consecutive output rows to touch at most three source rows: ry <= 1)
-  if (COND == 2 && C == 256 && a.rx * 31.f + 2.f <= 18.f && a.ry <= 1.f) {
-    dim3 grid((g.w + 31) / 32, (g.h + 1) / 2, g.B);
+  if (COND == 2 && C == 256 && a.rx * (dd::UPK_SEG - 1) + 2.f <= static_cast<float>(dd::UPK_SW) && a.ry <= 1.f) {
+    dim3 grid((g.w + dd::UPK_SEG - 1) / dd::UPK_SEG, (g.h + 1) / 2, g.B);
     dd::gn_apply_up_split_kernel<<<grid, 256, dd::UPK_SMEM, st>>>(a);
   } else {
     constexpr int PPB = 256 / (C / 8);
@@ -1490,9 +1521,9 @@ int run_swin(dd_engine* e, const float* rgb, float* const* feats_out, cudaStream
   Backbone& b = e->bb;
   const int B = e->cfg.batch;
   {
-    const int M0 = B * b.Hs[0] * b.Ws[0];
-    dd::patch_embed_kernel<192><<<(M0 + 7) / 8, 192, 0, st>>>(rgb, b.pe_w, b.pe_b, b.pe_g, b.pe_beta, b.X[0], B, b.H, b.W,
-                                                               b.Hs[0], b.Ws[0]);
+    const int segs = (b.Ws[0] + dd::PE_TOK - 1) / dd::PE_TOK;
+    dd::patch_embed_kernel<192><<<segs * b.Hs[0] * B, 192, 0, st>>>(rgb, b.pe_w, b.pe_b, b.pe_g, b.pe_beta, b.X[0], B, b.H,
+                                                                     b.W, b.Hs[0], b.Ws[0]);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
   }
@@ -1580,6 +1611,7 @@ int dd_create(const dd_config* cfg, dd_handle* out) {
   if (const char* v = getenv("DD_HALO_MASK")) e->halo_mask = atoi(v);
   if (const char* v = getenv("DD_PAIR_MASK")) e->pair_mask = atoi(v);
   if (const char* v = getenv("DD_GENPAIR")) e->genpair_mask = atoi(v);
+  if (const char* v = getenv("DD_SWAPHALO")) e->swaphalo_mask = atoi(v);
   e->want_clk_probe = getenv("DD_CLK_PROBE") != nullptr;
 #endif
   if (cudaMallocHost(&e->status_host, 64) != cudaSuccess ||
@@ -2280,9 +2312,19 @@ int dd_conv3x3(dd_handle h, const float* x, const float* w, const float* b, floa
     __half* wsw = wswap;
     dd::pack_swap_weight_kernel<<<128, 256, 0, st>>>(w, wsw, cout, cin, sw);
     CUDA_TRY(cudaGetLastError());
-    if ((rc = make_patch_map(&mp_hi, hi, batch, height, width, cin, bk))) return rc;
-    if ((rc = make_patch_map(&mp_lo, lo, batch, height, width, cin, bk))) return rc;
+    const bool swap_halo = (h->cfg.flags & DD_FLAG_HALO_CONV) && bk == 32 && h->swaphalo_mask != 0;
+    if (swap_halo) {
+      if ((rc = make_swap_strip_map(&mp_hi, hi, batch, height, width, cin, bk))) return rc;
+      if ((rc = make_swap_strip_map(&mp_lo, lo, batch, height, width, cin, bk))) return rc;
+    } else {
+      if ((rc = make_patch_map(&mp_hi, hi, batch, height, width, cin, bk))) return rc;
+      if ((rc = make_patch_map(&mp_lo, lo, batch, height, width, cin, bk))) return rc;
+    }
     if ((rc = make_w_map(&mw, wsw, 128, cin, bk))) return rc;
+    if (swap_halo) {
+      err = sid == 3 ? launch_swap<256, 64, 32, dd::EPI_F32, true>(mp_hi, mp_lo, mw, a, h->sm_count, st)
+                     : launch_swap<64, 16, 32, dd::EPI_F32, true>(mp_hi, mp_lo, mw, a, h->sm_count, st);
+    } else
     switch (sid) {
       case 0: err = launch_swap<16, 64, 16, dd::EPI_F32>(mp_hi, mp_lo, mw, a, h->sm_count, st); break;
       case 3: err = launch_swap<256, 64, 32, dd::EPI_F32>(mp_hi, mp_lo, mw, a, h->sm_count, st); break;

@@ -319,7 +319,9 @@ __global__ void __launch_bounds__(256) gn_apply_split_kernel(const ApplyArgs a) 
 // in shared memory (no registers, no per-thread gather loop - a 36-iteration staging loop made the previous version
 // latency-bound at 35 % of HBM bandwidth), while the threads already stream their conv outputs.  The time embedding is
 // constant over space and the bilinear weights sum to one, so it is added after the interpolation.
-constexpr int UPK_SEG = 32, UPK_SW = 18, UPK_ROWS = 3;
+// 16-pixel segments: 3 x 10 source pixels = 31 KB of staging per block -> 6 blocks per SM (32-pixel segments needed 57 KB: 3 blocks,
+// 23 % occupancy and 64 % of the HBM rate in ncu, round 2)
+constexpr int UPK_SEG = 16, UPK_SW = 10, UPK_ROWS = 3;
 constexpr int UPK_SMEM = UPK_ROWS * UPK_SW * 256 * 4 + 2 * 256 * 4 + 16;
 __global__ void __launch_bounds__(256) gn_apply_up_split_kernel(const ApplyArgs a) {
   constexpr int C = 256, SEG = UPK_SEG, SW = UPK_SW;

@@ -34,19 +34,19 @@ def _head_sd(head):
 
 
 # ------------------------------------------------------------------------------------------------ single layers
-@pytest.mark.parametrize("path", ["classic", "halo", "pair", "swap", "simt", "pair_f8"])
+@pytest.mark.parametrize("path", ["classic", "halo", "pair", "swap", "swap_halo", "simt", "pair_f8"])
 @pytest.mark.parametrize("cin,cout", SHAPES)
 def test_conv3x3_all_hot_path_shapes(cin, cout, path):
     """3-pass fp16 split on tcgen05 — classic 8x16-tile kernel, row-halo-reuse kernel, its CTA-pair (cta_group::2,
     M = 256) variant for Cout = 256 (odd tile counts leave the second CTA of the last pair a zero-filled tile),
-    swapped-operand kernel for the narrow layers — and the fp32 CUDA-core check path, vs an fp64 reference; ragged
-    tiles, a single tile, sub-tile images."""
+    swapped-operand kernel for the narrow layers (plain, and with row-halo strips for its pixel operand) — and the fp32
+    CUDA-core check path, vs an fp64 reference; ragged tiles, a single tile, sub-tile images."""
     if path == "pair_f8" and (cin, cout) != (256, 256):
         pytest.skip("fp8 correction products serve the 256 -> 256 layers")
     # pair_f8: correction products as e4m3 MMAs (DD_FLAG_FP8_CORR): ~2^-15 per product instead of ~2^-22
     tol = 3e-4 if path == "pair_f8" else 3e-5
     eng = dd.DenoiseEngine("swin", 1, (8, 16), (4, 8), 2, DEV, cuda_graph=False, simt_conv=path == "simt",
-                           halo_conv=path in ("halo", "pair", "pair_f8"), swap_narrow=path == "swap",
+                           halo_conv=path in ("halo", "pair", "pair_f8", "swap_halo"), swap_narrow=path in ("swap", "swap_halo"),
                            pair_wide=path in ("pair", "pair_f8"), fp8_corr=path == "pair_f8")
     for (B, H, W) in [(2, 24, 40), (1, 8, 16), (1, 13, 21), (1, 5, 9), (2, 57, 76)]:
         g = torch.Generator().manual_seed(cin * 1000 + cout + H)
