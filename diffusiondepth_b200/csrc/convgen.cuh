@@ -356,15 +356,20 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
 #pragma unroll
             for (int j = 0; j < 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
-          __align__(16) __half hi[16];
-          __align__(16) __half lo[16];
+          // split two channels at a time (one packed fp32 -> fp16x2 conversion each way); the range check is one running
+          // max instead of a compare per element
+          __align__(16) __half2 hi[8];
+          __align__(16) __half2 lo[8];
+          float amax = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float sc = v[j] * p.split_scale;
-            overflow |= (fabsf(sc) > 60000.f);
-            hi[j] = __float2half_rn(sc);
-            lo[j] = __float2half_rn(sc - __half2float(hi[j]));
+          for (int j = 0; j < 8; ++j) {
+            const float s0 = v[2 * j] * p.split_scale, s1 = v[2 * j + 1] * p.split_scale;
+            amax = fmaxf(amax, fmaxf(fabsf(s0), fabsf(s1)));
+            hi[j] = __floats2half2_rn(s0, s1);
+            const float2 back = __half22float2(hi[j]);
+            lo[j] = __floats2half2_rn(s0 - back.x, s1 - back.y);
           }
+          overflow |= !(amax <= 60000.f);  // also catches NaN
           uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o_lane);
           uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o_lane);
 #pragma unroll
