@@ -199,6 +199,8 @@ cudaError_t configure_all_kernels() {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(dd::gn_apply_up_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 dd::UPK_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::window_attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::WAU_SMEM)) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<16, 64, 16>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<64, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<256, 256, 32>()) != cudaSuccess) return e;
@@ -452,6 +454,7 @@ struct dd_engine {
   int probe_fp8 = 0, swap_mask = -1, halo_mask = -1, pair_mask = -1;
   int genpair_mask = 1;  // DD_GENPAIR=0 (probes build): producer convs / GEMMs on single CTAs
   int swaphalo_mask = 1; // DD_SWAPHALO=0 (probes build): narrow layers on the plain swapped-operand kernel
+  int attn_simt = 0;     // DD_ATTN_SIMT=1 (probes build): window attention on the fp32 CUDA-core kernel
   bool want_clk_probe = false;
   bool weights_ready = false;
   std::map<std::string, Raw> raw;
@@ -1548,7 +1551,13 @@ int run_swin(dd_engine* e, const float* rgb, float* const* feats_out, cudaStream
       aa.shift = (k & 1) ? ws / 2 : 0;
       aa.Hp = Hp; aa.Wp = Wp; aa.nWx = Wp / ws; aa.nWy = Hp / ws;
       aa.status = e->status;
-      dd::window_attention_kernel<<<B * aa.nWx * aa.nWy * nH, 64, 0, st>>>(aa);
+      if ((e->cfg.flags & DD_FLAG_SIMT_CONV) || (nH & 1) || e->attn_simt) {  // fp32 CUDA-core check path
+        dd::window_attention_kernel<<<B * aa.nWx * aa.nWy * nH, 64, 0, st>>>(aa);
+      } else {  // tcgen05: pairs of heads of one window per M = 128 tile, two persistent CTAs per SM
+        const int pairs = B * aa.nWx * aa.nWy * (nH / 2);
+        const int grid = pairs < 2 * e->sm_count ? pairs : 2 * e->sm_count;
+        dd::window_attention_umma_kernel<<<grid, 128, dd::WAU_SMEM, st>>>(aa, pairs);
+      }
       e->launches++;
       CUDA_TRY(cudaGetLastError());
       if ((rc = run_gemm(e, Wt.proj, b.AP, M, 0, x, x, nullptr, st))) return rc;      // x += proj(attn)
@@ -1612,6 +1621,7 @@ int dd_create(const dd_config* cfg, dd_handle* out) {
   if (const char* v = getenv("DD_PAIR_MASK")) e->pair_mask = atoi(v);
   if (const char* v = getenv("DD_GENPAIR")) e->genpair_mask = atoi(v);
   if (const char* v = getenv("DD_SWAPHALO")) e->swaphalo_mask = atoi(v);
+  if (const char* v = getenv("DD_ATTN_SIMT")) e->attn_simt = atoi(v);
   e->want_clk_probe = getenv("DD_CLK_PROBE") != nullptr;
 #endif
   if (cudaMallocHost(&e->status_host, 64) != cudaSuccess ||

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(E) patch_embed_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, float* __restrict__ x, int B, int H,
                                                         int W, int Hp, int Wp) {
   constexpr int TOK = 8;  // tokens per inner group
-  __shared__ float patch[PE_TOK][49];  // [token][c*16 + ky*4 + kx], padded row
+  __shared__ __align__(16) float patch[PE_TOK][48];  // [token][c*16 + ky*4 + kx]: read back as broadcast float4s
   __shared__ float red[2][TOK][E / 32];
   const int segs = (Wp + PE_TOK - 1) / PE_TOK;
   const int seg = blockIdx.x % segs, py = (blockIdx.x / segs) % Hp, b = blockIdx.x / (segs * Hp);
@@ -100,7 +100,13 @@ __global__ void __launch_bounds__(E) patch_embed_kernel(const float* __restrict_
     for (int tk = 0; tk < TOK; ++tk) {
       float a = be;
 #pragma unroll
-      for (int k = 0; k < 48; ++k) a = fmaf(patch[g0 + tk][k], wr[k], a);
+      for (int k4 = 0; k4 < 12; ++k4) {  // one 16-byte broadcast load feeds four FMAs
+        const float4 pv = *reinterpret_cast<const float4*>(&patch[g0 + tk][4 * k4]);
+        a = fmaf(pv.x, wr[4 * k4], a);
+        a = fmaf(pv.y, wr[4 * k4 + 1], a);
+        a = fmaf(pv.z, wr[4 * k4 + 2], a);
+        a = fmaf(pv.w, wr[4 * k4 + 3], a);
+      }
       acc[tk] = a;
     }
 #pragma unroll
@@ -306,6 +312,280 @@ __global__ void __launch_bounds__(64) window_attention_kernel(const AttnArgs a) 
     dl[d] = reinterpret_cast<const uint4*>(ll)[d];
   }
   if (ov) atomicOr(a.status, 1);
+}
+
+
+// ------------------------------------------------------------------ (shifted) 7x7 window attention on tcgen05
+// QK^T and PV as 3-pass fp16-split UMMAs with fp32 accumulators in TMEM; softmax in registers.  One persistent CTA
+// (128 threads = 128 TMEM lanes) walks PAIRS of (window, head) units — the two units of a pair are two consecutive
+// heads of the same window — and thread t owns row t: unit t / 64, query t % 64 (49 real rows, 15 zero rows).
+//   gather   q (pre-scaled by head_dim^-0.5), k, v rows from the fp32 qkv stream (padded tokens carry the qkv bias,
+//            exactly as in window_attention_kernel), split into fp16 hi / lo planes and WRITE them into shared memory in
+//            the swizzled K-major layouts the tensor core reads: Q [128 x 32] and K_u [64 x 32] with 64-byte rows
+//            (16-byte chunk c of row r at chunk c ^ ((r >> 1) & 3)), V_u transposed [32 dims x 64 keys] with 128-byte
+//            rows (chunk c ^ (r & 7));
+//   S        D_S[u] (TMEM columns 64 u ..) = Q K_u^T: 3 passes x 2 K-steps, M = 128, N = 64; only unit u's 64 rows of D_S[u]
+//            are meaningful (the other half is the cross product with the other head and is never read);
+//   softmax  each thread loads its row (tcgen05.ld), adds relative-position bias and the finite -100 shift mask, takes
+//            the softmax over the 49 keys in fp32 and writes P (x 4096) as hi / lo planes [128 x 64], 128-byte rows;
+//   O        D_O[u] (TMEM columns 128 + 32 u ..) = P V_u: 3 passes x 4 K-steps, M = 128, N = 32;
+//   store    each thread loads its 32 outputs, splits them and writes the proj GEMM's input planes.
+// 36 small MMAs per pair (~105 cycles each: N <= 64 is floor-bound) against ~2 x 3.1 k SM cycles of fp32 FMAs in the
+// SIMT kernel; two CTAs per SM overlap one's softmax with the other's MMAs.  Replaces reference swin.py:150-189 / 250-325.
+constexpr int WAU_SMEM = 16384 /*Q*/ + 16384 /*K*/ + 16384 /*Vt*/ + 32768 /*P*/ + 1024 /*align*/ + 1024 /*ctrl*/;
+__device__ __forceinline__ void wau_split8(const float* v, float scale, uint4& hi, uint4& lo, bool& ov) {
+  __align__(16) __half2 h[4];
+  __align__(16) __half2 l[4];
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float s0 = v[2 * j] * scale, s1 = v[2 * j + 1] * scale;
+    amax = fmaxf(amax, fmaxf(fabsf(s0), fabsf(s1)));
+    h[j] = __floats2half2_rn(s0, s1);
+    const float2 b = __half22float2(h[j]);
+    l[j] = __floats2half2_rn(s0 - b.x, s1 - b.y);
+  }
+  ov |= !(amax <= 60000.f);
+  hi = *reinterpret_cast<const uint4*>(h);
+  lo = *reinterpret_cast<const uint4*>(l);
+}
+__global__ void __launch_bounds__(128, 2) window_attention_umma_kernel(const AttnArgs a, int num_pairs) {
+  constexpr int WS = 7, N = 49, D = 32;
+  constexpr float kP = 4096.f;  // probabilities are split at this scale
+  extern __shared__ uint8_t wau_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wau_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                 // [plane][128 rows][64 B]
+  uint8_t* sK = smem + 16384;         // [unit][plane][64 rows][64 B]
+  uint8_t* sV = smem + 32768;         // [unit][plane][32 rows][128 B]
+  uint8_t* sP = smem + 49152;         // [plane][128 rows][128 B]
+  uint8_t* ctrl = smem + 81920;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ctrl);            // [0] S done, [1] O done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 16);
+  int* s_tok = reinterpret_cast<int*>(ctrl + 64);               // [49] source token or -1
+  int* s_reg = s_tok + 64;                                      // [49] shift-mask region id
+  const int t = threadIdx.x, warp = t >> 5;
+  const int u = t >> 6, i = t & 63;                             // unit within the pair, query row
+  if (t == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool leader_warp = (warp == 1);
+  const bool leader = leader_warp && elect_one();
+  constexpr uint32_t idesc_s = umma_idesc_f16(128, 64), idesc_o = umma_idesc_f16(128, 32);
+  const float qscale = rsqrtf(static_cast<float>(D));
+  const int heads_half = a.nH >> 1;
+  uint32_t phase = 0;
+  bool ov = false;
+  for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+    const int hp = pair % heads_half, win = pair / heads_half;
+    const int head = 2 * hp + u;
+    const int wx = win % a.nWx, wy = (win / a.nWx) % a.nWy, b = win / (a.nWx * a.nWy);
+    if (t < N) {
+      const int iy = t / WS, ix = t % WS;
+      const int sy = wy * WS + iy, sx = wx * WS + ix;  // coordinates in the rolled, padded frame
+      int reg = 0;
+      if (a.shift > 0) {
+        const int ry = sy < a.Hp - WS ? 0 : (sy < a.Hp - a.shift ? 1 : 2);
+        const int rx = sx < a.Wp - WS ? 0 : (sx < a.Wp - a.shift ? 1 : 2);
+        reg = ry * 3 + rx;
+      }
+      const int py = (sy + a.shift) % a.Hp, px = (sx + a.shift) % a.Wp;  // torch.roll(x, -shift)[i] = x[(i+shift) % n]
+      s_tok[t] = (py < a.H && px < a.W) ? (b * a.H + py) * a.W + px : -1;
+      s_reg[t] = reg;
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- gather + split + swizzled operand writes
+    const int tok = i < N ? s_tok[i] : -1;
+    {
+      const float* base = (tok >= 0 ? a.qkv + static_cast<size_t>(tok) * 3 * a.C : a.qkv_bias) + head * D;
+      const uint32_t rq = static_cast<uint32_t>(t), rk = static_cast<uint32_t>(i);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // 16-byte chunks of 8 dims
+        float q8[8], k8[8];
+#pragma unroll
+        for (int h4 = 0; h4 < 2; ++h4) {
+          float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), ka = qa;
+          if (i < N) {
+            qa = *reinterpret_cast<const float4*>(base + 8 * c + 4 * h4);
+            ka = *reinterpret_cast<const float4*>(base + a.C + 8 * c + 4 * h4);
+          }
+          q8[4 * h4] = qa.x * qscale; q8[4 * h4 + 1] = qa.y * qscale; q8[4 * h4 + 2] = qa.z * qscale; q8[4 * h4 + 3] = qa.w * qscale;
+          k8[4 * h4] = ka.x; k8[4 * h4 + 1] = ka.y; k8[4 * h4 + 2] = ka.z; k8[4 * h4 + 3] = ka.w;
+        }
+        uint4 hi, lo;
+        wau_split8(q8, a.scale_out, hi, lo, ov);
+        const uint32_t oq = rq * 64 + ((static_cast<uint32_t>(c) ^ ((rq >> 1) & 3u)) << 4);
+        *reinterpret_cast<uint4*>(sQ + oq) = hi;
+        *reinterpret_cast<uint4*>(sQ + 8192 + oq) = lo;
+        wau_split8(k8, a.scale_out, hi, lo, ov);
+        const uint32_t ok = rk * 64 + ((static_cast<uint32_t>(c) ^ ((rk >> 1) & 3u)) << 4);
+        *reinterpret_cast<uint4*>(sK + u * 8192 + ok) = hi;
+        *reinterpret_cast<uint4*>(sK + u * 8192 + 4096 + ok) = lo;
+      }
+      // V transposed: element (dim d, key i) of unit u -> row d (128 B), 16-byte chunk (i >> 3) ^ (d & 7), half (i & 7)
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < N) va = *reinterpret_cast<const float4*>(base + 2 * a.C + 4 * d4);
+        const float vv[4] = {va.x, va.y, va.z, va.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t d = 4 * d4 + j;
+          const float sc = vv[j] * a.scale_out;
+          ov |= !(fabsf(sc) <= 60000.f);
+          const __half h = __float2half_rn(sc);
+          const __half l = __float2half_rn(sc - __half2float(h));
+          const uint32_t o = d * 128 + (((static_cast<uint32_t>(i) >> 3) ^ (d & 7u)) << 4) + ((static_cast<uint32_t>(i) & 7u) << 1);
+          *reinterpret_cast<__half*>(sV + u * 8192 + o) = h;
+          *reinterpret_cast<__half*>(sV + u * 8192 + 4096 + o) = l;
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---------------------------------------------------------------- S = Q K^T  (lo*hi, hi*hi, hi*lo per K-step)
+    if (leader_warp) {
+      tc_fence_after();
+      if (leader) {
+        const uint32_t q_hi = smem_u32(sQ), q_lo = q_hi + 8192;
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+          const uint32_t k_hi = smem_u32(sK) + uu * 8192, k_lo = k_hi + 4096;
+          const uint32_t d_s = tmem_base + uu * 64;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            umma_f16(d_s, umma_smem_desc(q_lo + k * 32, 64), umma_smem_desc(k_hi + k * 32, 64), idesc_s, k ? 1u : 0u);
+            umma_f16(d_s, umma_smem_desc(q_hi + k * 32, 64), umma_smem_desc(k_hi + k * 32, 64), idesc_s, 1u);
+            umma_f16(d_s, umma_smem_desc(q_hi + k * 32, 64), umma_smem_desc(k_lo + k * 32, 64), idesc_s, 1u);
+          }
+        }
+        umma_commit(&bar[0]);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bar[0], phase);
+    tc_fence_after();
+    // ---------------------------------------------------------------- softmax of row (u, i)
+    float pr[64];
+    {
+      uint32_t r0[32], r1[32];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(u * 64);
+      tmem_ld_32x32(taddr, r0);
+      tmem_ld_32x32(taddr + 32, r1);
+      tmem_ld_wait();
+      const float inv = 1.f / (a.scale_out * a.scale_out);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        pr[j] = __uint_as_float(r0[j]) * inv;
+        pr[32 + j] = __uint_as_float(r1[j]) * inv;
+      }
+    }
+    if (i < N) {
+      const int iy = i / WS, ix = i - iy * WS;
+      const int my_reg = s_reg[i];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const int jy = j / WS, jx = j - jy * WS;
+        const int rel = (iy - jy + WS - 1) * (2 * WS - 1) + (ix - jx + WS - 1);
+        float sv = pr[j] + __ldg(a.bias_table + rel * a.nH + head);
+        if (a.shift > 0 && my_reg != s_reg[j]) sv += -100.0f;
+        pr[j] = sv;
+        mx = fmaxf(mx, sv);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        pr[j] = expf(pr[j] - mx);
+        sum += pr[j];
+      }
+      const float rs = kP / sum;
+#pragma unroll
+      for (int j = 0; j < N; ++j) pr[j] *= rs;
+#pragma unroll
+      for (int j = N; j < 64; ++j) pr[j] = 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) pr[j] = 0.f;
+    }
+    {
+      const uint32_t rp = static_cast<uint32_t>(t);
+      bool dummy = false;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 hi, lo;
+        wau_split8(pr + 8 * c, 1.f, hi, lo, dummy);  // 0 <= P * 4096 <= 4096: always in range
+        const uint32_t o = rp * 128 + ((static_cast<uint32_t>(c) ^ (rp & 7u)) << 4);
+        *reinterpret_cast<uint4*>(sP + o) = hi;
+        *reinterpret_cast<uint4*>(sP + 16384 + o) = lo;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---------------------------------------------------------------- O = P V
+    if (leader_warp) {
+      tc_fence_after();
+      if (leader) {
+        const uint32_t p_hi = smem_u32(sP), p_lo = p_hi + 16384;
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+          const uint32_t v_hi = smem_u32(sV) + uu * 8192, v_lo = v_hi + 4096;
+          const uint32_t d_o = tmem_base + 128 + uu * 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(d_o, umma_smem_desc(p_lo + k * 32, 128), umma_smem_desc(v_hi + k * 32, 128), idesc_o, k ? 1u : 0u);
+            umma_f16(d_o, umma_smem_desc(p_hi + k * 32, 128), umma_smem_desc(v_hi + k * 32, 128), idesc_o, 1u);
+            umma_f16(d_o, umma_smem_desc(p_hi + k * 32, 128), umma_smem_desc(v_lo + k * 32, 128), idesc_o, 1u);
+          }
+        }
+        umma_commit(&bar[1]);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bar[1], phase);
+    tc_fence_after();
+    {
+      uint32_t ro[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(128 + u * 32), ro);
+      tmem_ld_wait();
+      if (tok >= 0) {  // padded query rows are cropped by the reference (:319-320); rows >= 49 do not exist
+        const float inv = 1.f / (kP * a.scale_out);
+        uint4* dh = reinterpret_cast<uint4*>(a.out_hi + static_cast<size_t>(tok) * a.C + head * D);
+        uint4* dl = reinterpret_cast<uint4*>(a.out_lo + static_cast<size_t>(tok) * a.C + head * D);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float o8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = __uint_as_float(ro[8 * c + j]) * inv;
+          uint4 hi, lo;
+          wau_split8(o8, a.scale_out, hi, lo, ov);
+          dh[c] = hi;
+          dl[c] = lo;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM rows and the operand tiles are free for the next pair
+    phase ^= 1;
+  }
+  if (ov) atomicOr(a.status, 1);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
 }
 
 }  // namespace dd

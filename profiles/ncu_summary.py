@@ -21,8 +21,9 @@ for path in sys.argv[1:]:
     rows = [r for r in csv.reader(open(path)) if len(r) > 20]
     hdr, units = rows[0], rows[1]
     idx = [(hdr.index(c), n) for c, n in COLS if c in hdr]
-    if first:
-        w.writerow(["file"] + [n + ("[" + units[i] + "]" if units[i] else "") for i, n in idx])
+    if first:  # same two header rows as the raw export: metric names, then units
+        w.writerow([hdr[i] for i, n in idx])
+        w.writerow([units[i] for i, n in idx])
         first = False
     for r in rows[2:]:
-        w.writerow([path.split("/")[-1]] + [(r[i][:70] if n == "kernel" else r[i]) for i, n in idx])
+        w.writerow([(r[i][:90] if n == "kernel" else r[i]) for i, n in idx])
