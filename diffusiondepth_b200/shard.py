@@ -76,9 +76,12 @@ class DepthGatherer:
         return slot
 
     def result(self, ticket: int) -> torch.Tensor:
+        out = self._bufs[ticket]
         if self._done[ticket] is not None:
-            torch.cuda.current_stream(self._bufs[ticket].device).wait_event(self._done[ticket])
-        return self._bufs[ticket]
+            cur = torch.cuda.current_stream(out.device)
+            cur.wait_event(self._done[ticket])
+            out.record_stream(cur)  # allocated on the side stream, consumed here: keep the block until this stream is done
+        return out
 
     def drain(self):
         if self._stream is not None:
