@@ -290,6 +290,14 @@ def main():
         sampler.start()
     ms = timed(step_resident, args.steps, "resident")
     clocks = sampler.stop() if sampler else None
+    if world > 1:
+        # the same steps WITHOUT the collective: each rank's own pace.  With it, every rank's clock stops when the slowest
+        # peer has delivered its last shard, so `resident` shows one number for all ranks; this one shows the spread
+        # (power-capped GPUs of one box differ by a few per cent) that bounds weak-scaling efficiency from outside.
+        def step_local():
+            with torch.no_grad():
+                return model(resident)["pred"]
+        timed(step_local, args.steps, "compute_only_no_gather")
     launches = eng.last_launch_count * args.steps
     value = B * world * args.steps / (ms / 1e3)
     step_e2e()

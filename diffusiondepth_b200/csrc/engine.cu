@@ -201,6 +201,8 @@ cudaError_t configure_all_kernels() {
                                 dd::UPK_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dd::window_attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 dd::WAU_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dd::DEC_SMEM)) != cudaSuccess)
+    return e;
   if ((e = configure_umma_all_epi<16, 64, 16>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<64, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<256, 256, 32>()) != cudaSuccess) return e;
@@ -989,7 +991,7 @@ int run_decoder(dd_engine* e, float* logit, float* depth, cudaStream_t st) {
   a.w = g.w;
   a.eps = 1e-6f;
   dim3 grid((2 * g.w + dd::DEC_TW - 1) / dd::DEC_TW, (2 * g.h + dd::DEC_TH - 1) / dd::DEC_TH, g.B);
-  dd::decoder_kernel<<<grid, 256, 0, st>>>(a);
+  dd::decoder_kernel<<<grid, 256, dd::DEC_SMEM, st>>>(a);
   e->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("decoder: ") + cudaGetErrorString(err));
@@ -1553,9 +1555,9 @@ int run_swin(dd_engine* e, const float* rgb, float* const* feats_out, cudaStream
       aa.status = e->status;
       if ((e->cfg.flags & DD_FLAG_SIMT_CONV) || (nH & 1) || e->attn_simt) {  // fp32 CUDA-core check path
         dd::window_attention_kernel<<<B * aa.nWx * aa.nWy * nH, 64, 0, st>>>(aa);
-      } else {  // tcgen05: pairs of heads of one window per M = 128 tile, two persistent CTAs per SM
+      } else {  // tcgen05: pairs of heads of one window per M = 128 tile, three persistent CTAs per SM
         const int pairs = B * aa.nWx * aa.nWy * (nH / 2);
-        const int grid = pairs < 2 * e->sm_count ? pairs : 2 * e->sm_count;
+        const int grid = pairs < 3 * e->sm_count ? pairs : 3 * e->sm_count;
         dd::window_attention_umma_kernel<<<grid, 128, dd::WAU_SMEM, st>>>(aa, pairs);
       }
       e->launches++;

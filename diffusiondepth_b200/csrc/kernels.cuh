@@ -314,13 +314,14 @@ __global__ void __launch_bounds__(256) gn_apply_split_kernel(const ApplyArgs a) 
 }
 
 // Swin-head variant of the above for C = 256 with the bilinear (align_corners=True) condition injection, tiled:
-// one block = 32 consecutive output pixels of TWO consecutive latent rows.  The <= 3 x 18 source pixels of the
-// condition map they interpolate from are contiguous 18 KB runs in NHWC: one cp.async.bulk per source row stages them
-// in shared memory (no registers, no per-thread gather loop - a 36-iteration staging loop made the previous version
-// latency-bound at 35 % of HBM bandwidth), while the threads already stream their conv outputs.  The time embedding is
-// constant over space and the bilinear weights sum to one, so it is added after the interpolation.
-// 16-pixel segments: 3 x 10 source pixels = 31 KB of staging per block -> 6 blocks per SM (32-pixel segments needed 57 KB: 3 blocks,
-// 23 % occupancy and 64 % of the HBM rate in ncu, round 2)
+// one block = UPK_SEG consecutive output pixels of TWO consecutive latent rows.  The <= 3 x UPK_SW source pixels of the
+// condition map they interpolate from are contiguous runs in NHWC: one cp.async.bulk per source row stages them in
+// shared memory (no registers, no per-thread gather loop - a 36-iteration staging loop made the first version
+// latency-bound at 35 % of HBM bandwidth), while the threads already stream their conv outputs.  The time embedding
+// enters every tap as in the reference ((cond + te) interpolated).
+// 16-pixel segments: 3 x 10 source pixels = 31 KB of staging per block -> 6 blocks per SM.  (32-pixel segments: 57 KB, 3
+// blocks, 23 % occupancy; the kernel ran 221 us = 64 % of the copy rate either way (ncu, round 2): with 51 % issue-active
+// the bilinear + split arithmetic shares the bound with HBM.)
 constexpr int UPK_SEG = 16, UPK_SW = 10, UPK_ROWS = 3;
 constexpr int UPK_SMEM = UPK_ROWS * UPK_SW * 256 * 4 + 2 * 256 * 4 + 16;
 __global__ void __launch_bounds__(256) gn_apply_up_split_kernel(const ApplyArgs a) {
@@ -609,18 +610,27 @@ struct DecoderArgs {
   float eps;
 };
 constexpr int DEC_TH = 8, DEC_TW = 32;
+constexpr int DEC_SMEM = ((DEC_TH / 2 + 2) * (DEC_TW / 2 + 2) * 16 + (DEC_TH + 2) * (DEC_TW + 2) * 20 + 4096 + 144 + 16) * 4;
+// Round 2 (ncu: the first version spent 618 us per call with the shared-memory pipe 96 % busy — scalar weight reads in
+// the transposed conv, two scalar reads per FMA in the final conv): the transposed conv walks the intermediate pixels
+// PARITY CLASS by parity class, so a warp's (ky, kx) taps and output-channel half are uniform and the folded weights come
+// in as broadcast float4s (2 x LDS.128 + 1 latent read per 8 FMAs); the final conv reads both the intermediate (row stride
+// 20 floats: conflict-free 16-byte reads) and its weights as float4s (8 x LDS.128 per 16 FMAs).
 __global__ void __launch_bounds__(256) decoder_kernel(const DecoderArgs a) {
   constexpr int LH = DEC_TH / 2 + 2, LW = DEC_TW / 2 + 2;  // latent patch 6 x 18
   constexpr int MH = DEC_TH + 2, MW = DEC_TW + 2;          // intermediate 10 x 34
-  __shared__ float s_lat[LH * LW][16];
-  __shared__ float s_mid[MH * MW][17];
-  __shared__ float s_wt[16 * 16 * 16];
-  __shared__ float s_wc[9 * 16];
-  __shared__ float s_bt[16];
+  constexpr int CH = MH / 2, CW = MW / 2, CPX = CH * CW;   // pixels per parity class: 5 x 17 = 85
+  constexpr int CPAD = 96;                                 // padded to whole warps
+  extern __shared__ __align__(16) float dec_smem[];  // DEC_SMEM bytes (above the 48 KB static limit)
+  float (*s_lat)[16] = reinterpret_cast<float (*)[16]>(dec_smem);
+  float (*s_mid)[20] = reinterpret_cast<float (*)[20]>(dec_smem + LH * LW * 16);
+  float* s_wt = dec_smem + LH * LW * 16 + MH * MW * 20;
+  float* s_wc = s_wt + 16 * 16 * 16;
+  float* s_bt = s_wc + 9 * 16;
   const int b = blockIdx.z;
   const int Y0 = blockIdx.y * DEC_TH, X0 = blockIdx.x * DEC_TW;
   const int H = 2 * a.h, W = 2 * a.w;
-  for (int i = threadIdx.x; i < 4096; i += 256) s_wt[i] = a.wt[i];
+  for (int i = threadIdx.x; i < 1024; i += 256) reinterpret_cast<float4*>(s_wt)[i] = reinterpret_cast<const float4*>(a.wt)[i];
   if (threadIdx.x < 144) s_wc[threadIdx.x] = a.wc[threadIdx.x];
   if (threadIdx.x < 16) s_bt[threadIdx.x] = a.bt[threadIdx.x];
   const int ly0 = Y0 / 2 - 1, lx0 = X0 / 2 - 1;
@@ -630,21 +640,26 @@ __global__ void __launch_bounds__(256) decoder_kernel(const DecoderArgs a) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (yy >= 0 && yy < a.h && xx >= 0 && xx < a.w)
       v = reinterpret_cast<const float4*>(a.x + ((static_cast<size_t>(b) * a.h + yy) * a.w + xx) * 16)[q];
-    s_lat[lp][q * 4 + 0] = v.x;
-    s_lat[lp][q * 4 + 1] = v.y;
-    s_lat[lp][q * 4 + 2] = v.z;
-    s_lat[lp][q * 4 + 3] = v.w;
+    *reinterpret_cast<float4*>(&s_lat[lp][q * 4]) = v;
   }
   __syncthreads();
-  // transposed conv: out(Y, X) gathers the 2x2 latent pixels iy = (Y + 1 - ky) / 2 with matching parity
-  for (int i = threadIdx.x; i < MH * MW * 4; i += 256) {
-    const int cq = i & 3, mp = i >> 2;  // 4 output channels per work item
-    const int Y = Y0 - 1 + mp / MW, X = X0 - 1 + mp % MW;
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
+  // transposed conv: out(Y, X) gathers the 2x2 latent pixels iy = (Y + 1 - ky) / 2 with matching parity.  Work item =
+  // (parity class, output-channel half, pixel of the class): 4 x 2 x 96 slots = 3 rounds of 256 threads, warp-uniform
+  // class and half.
+  for (int it = threadIdx.x; it < 8 * CPAD; it += 256) {
+    const int cls = it / (2 * CPAD), half = (it / CPAD) & 1, pi = it % CPAD;
+    if (pi >= CPX) continue;
+    // mid row my (0..9) <-> Y = Y0 - 1 + my; class parity py = (Y + 1) & 1 = (Y0 + my) & 1 -> Y0 is even: py = my & 1
+    const int py = cls >> 1, px = cls & 1;
+    const int my = 2 * (pi / CW) + py, mx = 2 * (pi % CW) + px;
+    const int Y = Y0 - 1 + my, X = X0 - 1 + mx;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
     if (Y >= 0 && Y < H && X >= 0 && X < W) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = s_bt[cq * 4 + j];
-      const int ky0 = (Y + 1) & 1, kx0 = (X + 1) & 1;
+      for (int j = 0; j < 8; ++j) o[j] = s_bt[half * 8 + j];
+      const int ky0 = (Y + 1) & 1, kx0 = (X + 1) & 1;  // == py, px (warp-uniform)
 #pragma unroll
       for (int a2 = 0; a2 < 2; ++a2) {
         const int ky = ky0 + 2 * a2;
@@ -656,22 +671,28 @@ __global__ void __launch_bounds__(256) decoder_kernel(const DecoderArgs a) {
           const int ix = (X + 1 - kx) / 2;
           if (X + 1 - kx < 0 || ix >= a.w) continue;
           const float* lp = s_lat[(iy - ly0) * LW + (ix - lx0)];
-          const float* wp = s_wt + ((ky * 4 + kx) * 16) * 16 + cq * 4;
+          const float* wp = s_wt + ((ky * 4 + kx) * 16) * 16 + half * 8;
 #pragma unroll
-          for (int ci = 0; ci < 16; ++ci) {
-            const float v = lp[ci];
-            o[0] = fmaf(v, wp[ci * 16 + 0], o[0]);
-            o[1] = fmaf(v, wp[ci * 16 + 1], o[1]);
-            o[2] = fmaf(v, wp[ci * 16 + 2], o[2]);
-            o[3] = fmaf(v, wp[ci * 16 + 3], o[3]);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 lv = *reinterpret_cast<const float4*>(lp + 4 * c4);
+            const float l4[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              const float4 w0 = *reinterpret_cast<const float4*>(wp + (4 * c4 + cc) * 16);
+              const float4 w1 = *reinterpret_cast<const float4*>(wp + (4 * c4 + cc) * 16 + 4);
+              const float v = l4[cc];
+              o[0] = fmaf(v, w0.x, o[0]); o[1] = fmaf(v, w0.y, o[1]); o[2] = fmaf(v, w0.z, o[2]); o[3] = fmaf(v, w0.w, o[3]);
+              o[4] = fmaf(v, w1.x, o[4]); o[5] = fmaf(v, w1.y, o[5]); o[6] = fmaf(v, w1.z, o[6]); o[7] = fmaf(v, w1.w, o[7]);
+            }
           }
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s_mid[mp][cq * 4 + j] = o[j];
+    float* mp = s_mid[my * MW + mx] + half * 8;
+    *reinterpret_cast<float4*>(mp) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(mp + 4) = make_float4(o[4], o[5], o[6], o[7]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < DEC_TH * DEC_TW; i += 256) {
@@ -683,7 +704,11 @@ __global__ void __launch_bounds__(256) decoder_kernel(const DecoderArgs a) {
     for (int tap = 0; tap < 9; ++tap) {
       const float* mp = s_mid[(yy + tap / 3) * MW + xx + tap % 3];
 #pragma unroll
-      for (int ci = 0; ci < 16; ++ci) z = fmaf(mp[ci], s_wc[tap * 16 + ci], z);
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 mv = *reinterpret_cast<const float4*>(mp + 4 * c4);
+        const float4 wv = *reinterpret_cast<const float4*>(s_wc + tap * 16 + 4 * c4);
+        z = fmaf(mv.x, wv.x, z); z = fmaf(mv.y, wv.y, z); z = fmaf(mv.z, wv.z, z); z = fmaf(mv.w, wv.w, z);
+      }
     }
     const size_t o = (static_cast<size_t>(b) * H + Y) * W + X;
     if (a.logit) a.logit[o] = z;

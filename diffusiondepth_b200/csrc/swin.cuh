@@ -328,11 +328,13 @@ __global__ void __launch_bounds__(64) window_attention_kernel(const AttnArgs a) 
 //            are meaningful (the other half is the cross product with the other head and is never read);
 //   softmax  each thread loads its row (tcgen05.ld), adds relative-position bias and the finite -100 shift mask, takes
 //            the softmax over the 49 keys in fp32 and writes P (x 4096) as hi / lo planes [128 x 64], 128-byte rows;
-//   O        D_O[u] (TMEM columns 128 + 32 u ..) = P V_u: 3 passes x 4 K-steps, M = 128, N = 32;
+//   O        D_O[u] (TMEM columns 32 u .., over S) = P V_u: 3 passes x 4 K-steps, M = 128, N = 32;
 //   store    each thread loads its 32 outputs, splits them and writes the proj GEMM's input planes.
 // 36 small MMAs per pair (~105 cycles each: N <= 64 is floor-bound) against ~2 x 3.1 k SM cycles of fp32 FMAs in the
-// SIMT kernel; two CTAs per SM overlap one's softmax with the other's MMAs.  Replaces reference swin.py:150-189 / 250-325.
-constexpr int WAU_SMEM = 16384 /*Q*/ + 16384 /*K*/ + 16384 /*Vt*/ + 32768 /*P*/ + 1024 /*align*/ + 1024 /*ctrl*/;
+// SIMT kernel; three CTAs per SM overlap one's softmax with the others' gathers and MMAs.  Replaces reference swin.py:150-189 / 250-325.
+// P re-uses the Q / K tiles (they are dead once the S MMAs have completed) and O re-uses the S columns of TMEM (every row of S is
+// in registers by then): 50 KB of shared memory and 128 TMEM columns per CTA, so three CTAs fit an SM (registers: 168 per thread).
+constexpr int WAU_SMEM = 32768 /*Q + K, then P*/ + 16384 /*Vt*/ + 1024 /*align*/ + 1024 /*ctrl*/;
 __device__ __forceinline__ void wau_split8(const float* v, float scale, uint4& hi, uint4& lo, bool& ov) {
   __align__(16) __half2 h[4];
   __align__(16) __half2 l[4];
@@ -349,16 +351,16 @@ __device__ __forceinline__ void wau_split8(const float* v, float scale, uint4& h
   hi = *reinterpret_cast<const uint4*>(h);
   lo = *reinterpret_cast<const uint4*>(l);
 }
-__global__ void __launch_bounds__(128, 2) window_attention_umma_kernel(const AttnArgs a, int num_pairs) {
+__global__ void __launch_bounds__(128, 3) window_attention_umma_kernel(const AttnArgs a, int num_pairs) {
   constexpr int WS = 7, N = 49, D = 32;
   constexpr float kP = 4096.f;  // probabilities are split at this scale
   extern __shared__ uint8_t wau_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wau_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                 // [plane][128 rows][64 B]
   uint8_t* sK = smem + 16384;         // [unit][plane][64 rows][64 B]
+  uint8_t* sP = smem;                 // [plane][128 rows][128 B]: over Q and K, written after the S MMAs have completed
   uint8_t* sV = smem + 32768;         // [unit][plane][32 rows][128 B]
-  uint8_t* sP = smem + 49152;         // [plane][128 rows][128 B]
-  uint8_t* ctrl = smem + 81920;
+  uint8_t* ctrl = smem + 49152;
   uint64_t* bar = reinterpret_cast<uint64_t*>(ctrl);            // [0] S done, [1] O done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 16);
   int* s_tok = reinterpret_cast<int*>(ctrl + 64);               // [49] source token or -1
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(128, 2) window_attention_umma_kernel(const Att
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(128, 2) window_attention_umma_kernel(const Att
 #pragma unroll
         for (int uu = 0; uu < 2; ++uu) {
           const uint32_t v_hi = smem_u32(sV) + uu * 8192, v_lo = v_hi + 4096;
-          const uint32_t d_o = tmem_base + 128 + uu * 32;
+          const uint32_t d_o = tmem_base + uu * 32;  // over the S columns: all of S is in registers by now
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             umma_f16(d_o, umma_smem_desc(p_lo + k * 32, 128), umma_smem_desc(v_hi + k * 32, 128), idesc_o, k ? 1u : 0u);
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(128, 2) window_attention_umma_kernel(const Att
     tc_fence_after();
     {
       uint32_t ro[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(128 + u * 32), ro);
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(u * 32), ro);
       tmem_ld_wait();
       if (tok >= 0) {  // padded query rows are cropped by the reference (:319-320); rows >= 49 do not exist
         const float inv = 1.f / (kP * a.scale_out);
@@ -584,7 +586,7 @@ __global__ void __launch_bounds__(128, 2) window_attention_umma_kernel(const Att
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 

@@ -1,10 +1,11 @@
 """Depth <-> latent codec registry (reference src/model/ops/depth_transform.py).
 
 Only the codec the shipped DDIM heads use is provided: `DeepDepthTransformWithUpsampling(hidden=16)`.
-`t()` (encoder, :29-31) feeds the loop nothing but its output *shape* and runs as plain torch ops;
-`inv_t()` (decoder, :33-35) is on the hot path — the heads route it through the CUDA engine
-(`DenoiseEngine.denoise_decode` / `.decode`); the torch expression below exists for API parity when a
-caller invokes `inv_t` directly on a tensor."""
+This module is the PARAMETER CONTAINER with the reference's key layout.  Inside a head's forward both directions run in
+the CUDA engine: `t()` (encoder, :29-31; its value is only returned as `pred_init`) through `dd_encode`, `inv_t()`
+(decoder, :33-35, on the hot path) through `dd_denoise_decode` / `dd_decode` (`DenoiseEngine.encode / .decode`).  The
+torch expressions below exist for API parity when a caller invokes `t` / `inv_t` directly on a tensor (and for the
+torch-op fallback of architectures the engine does not instantiate)."""
 import torch
 import torch.nn as nn
 

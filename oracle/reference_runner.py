@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — run the *real* reference model (oracle/ref_import.py) with an injected
 initial latent and capture the internal tensors parity is judged on (condition map, final latent,
-decoder logit).  Needs /root/reference; used by oracle/make_golden.py and tests/test_oracle_vs_reference.py."""
+decoder logit).  Needs /root/reference; used by oracle/make_golden.py and tests/test_oracle_golden.py."""
 import contextlib
 
 import torch
