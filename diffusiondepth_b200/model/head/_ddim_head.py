@@ -13,6 +13,7 @@ works both as `diffusiondepth_b200.model` and as the reference's top-level `mode
 `src/`, tested by tests/test_dropin.py)."""
 import collections
 import copy
+import threading
 import weakref
 from typing import Dict, Optional, Tuple
 
@@ -142,6 +143,7 @@ class DDIMHeadBase(nn.Module):
         self.__dict__['_engines'] = collections.OrderedDict()  # key -> DenoiseEngine, least recently used first
         self.__dict__['_packed'] = {}                          # key -> (tensor list, signature) of the packed weights
         self.__dict__['_pools'] = {}                           # device -> WorkspacePool
+        self.__dict__['_lock'] = threading.RLock()             # nn.DataParallel replicas (threads) share the three dicts
 
     def invalidate_engines(self):
         """Close every engine (call after replacing Parameter OBJECTS; in-place updates, load_state_dict and .to() are
@@ -156,7 +158,7 @@ class DDIMHeadBase(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_engines", "_packed", "_pools", "_backbone_ref"):
+            if k in ("_engines", "_packed", "_pools", "_backbone_ref", "_lock"):
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         new.__dict__['_backbone_ref'] = None
@@ -263,6 +265,10 @@ class DDIMHeadBase(nn.Module):
     def _engine(self, batch, latent_hw, cond_hw, device, feats=None, image_hw=None, backbone=None) -> DenoiseEngine:
         """feats: backbone feature maps, or a (channels, sizes) pyramid spec -> native neck/FPN;
         image_hw: additionally run the backbone natively (`backbone`: the module holding its parameters)."""
+        with self._lock:
+            return self._engine_locked(batch, latent_hw, cond_hw, device, feats, image_hw, backbone)
+
+    def _engine_locked(self, batch, latent_hw, cond_hw, device, feats, image_hw, backbone) -> DenoiseEngine:
         native = feats is not None
         if native and not isinstance(feats, tuple):
             feats = ([f.shape[1] for f in feats], [tuple(f.shape[-2:]) for f in feats])
