@@ -1555,9 +1555,9 @@ int run_swin(dd_engine* e, const float* rgb, float* const* feats_out, cudaStream
       aa.status = e->status;
       if ((e->cfg.flags & DD_FLAG_SIMT_CONV) || (nH & 1) || e->attn_simt) {  // fp32 CUDA-core check path
         dd::window_attention_kernel<<<B * aa.nWx * aa.nWy * nH, 64, 0, st>>>(aa);
-      } else {  // tcgen05: pairs of heads of one window per M = 128 tile, three persistent CTAs per SM
+      } else {  // tcgen05: pairs of heads of one window per M = 128 tile, four persistent CTAs per SM
         const int pairs = B * aa.nWx * aa.nWy * (nH / 2);
-        const int grid = pairs < 3 * e->sm_count ? pairs : 3 * e->sm_count;
+        const int grid = pairs < 4 * e->sm_count ? pairs : 4 * e->sm_count;
         dd::window_attention_umma_kernel<<<grid, 128, dd::WAU_SMEM, st>>>(aa, pairs);
       }
       e->launches++;
