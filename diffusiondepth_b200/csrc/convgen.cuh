@@ -15,9 +15,11 @@ namespace dd {
 struct GenConvArgs {
   int B, H, W;
   int tiles_x, tiles_y, m_tiles, n_tiles;
-  int kc0, kc1;       // GEN_BK-channel chunks taken from source 0, then source 1
+  int kc0, kc1;       // GEN_BK-channel chunks taken from source 0, then source 1 (ceil: a partial last chunk is completed
+                      // with zeros by TMA's out-of-bounds fill, on the activation AND the weight side)
+  int c0_ch;          // real channel count of source 0 = weight K offset of source 1's first channel
   int taps;           // 1 (1x1) or 9 (3x3, pad 1)
-  int cout;           // total output channels (n_tiles * NT)
+  int cout;           // total output channels (any multiple of 8; n_tiles = ceil(cout / NT), columns >= cout are dropped)
   const float* shift; // [cout] bias / folded BN shift
   float acc_scale;
   int relu;           // activation: 0 none, 1 ReLU, 2 exact (erf) GELU
@@ -144,14 +146,16 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* s = stage_ptr(stage);
           const int ax = x0 * p.stride + dx, ay = y0 * p.stride + dy;
+          // weight K coordinate of this chunk: source 1's channels start right after source 0's REAL channels
+          const int kw = kc < p.kc0 ? kc * C::BK : p.c0_ch + (kc - p.kc0) * C::BK;
           if (leader) {
             if constexpr (PAIR) {
               const uint32_t lead = mapa_u32(smem_u32(&full_bar[stage]), 0);
               const int brow = nt * NT + static_cast<int>(rank) * C::B_ROWS;  // this CTA's half of the N tile
               if (!act) {
                 mbar_arrive_expect_tx_cluster(lead, 2 * C::B_BYTES);
-                tma_load_3d_pair(s + 2 * C::A_BYTES, &tmB_hi, lead, kc * C::BK, brow, tap);
-                tma_load_3d_pair(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, lead, kc * C::BK, brow, tap);
+                tma_load_3d_pair(s + 2 * C::A_BYTES, &tmB_hi, lead, kw, brow, tap);
+                tma_load_3d_pair(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, lead, kw, brow, tap);
               } else if (kc < p.kc0) {
                 mbar_arrive_expect_tx_cluster(lead, 2 * C::A_BYTES);
                 tma_load_4d_pair(s, &tmA0_hi, lead, kc * C::BK, ax, ay, img);
@@ -163,8 +167,8 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
               }
             } else if (!act) {
               mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_BYTES);
-              tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kc * C::BK, nt * NT, tap);
-              tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kc * C::BK, nt * NT, tap);
+              tma_load_3d(s + 2 * C::A_BYTES, &tmB_hi, &full_bar[stage], kw, nt * NT, tap);
+              tma_load_3d(s + 2 * C::A_BYTES + C::B_BYTES, &tmB_lo, &full_bar[stage], kw, nt * NT, tap);
             } else if (kc < p.kc0) {
               mbar_arrive_expect_tx(&full_bar[stage], 2 * C::A_BYTES);
               tma_load_4d(s, &tmA0_hi, &full_bar[stage], kc * C::BK, ax, ay, img);
@@ -271,6 +275,8 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
       for (int ci = grp; ci < NCH; ci += 4) {
         const int ch0 = ci * 16;
         const int n0 = nt * NT + ch0;
+        if (n0 >= p.cout) break;  // columns past the last real output channel (cout not a multiple of NT): zero weights
+        const int nvalid = p.cout - n0;  // >= 8, multiple of 8; < 16 only in the last chunk of such a layer
         uint32_t rr[16];
         tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * NT + ch0), rr);
         tmem_ld_wait();
@@ -291,20 +297,21 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
                             __uint_as_float(rr[4 * sl + 3]));
           __syncwarp();
           const int sl = lane & 3;  // this lane's float4 slot: channels n0 + 4 sl .. + 3
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0) + sl);
+          const bool col_ok = 4 * sl < nvalid;
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0) + sl);  // shift[] is padded to n_tiles * NT
           uint32_t o[4];
           float4 ad[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // rows (lane >> 2) + 8 k: issue the addend loads before any store
             const int row = (lane >> 2) + 8 * k;
             o[k] = __shfl_sync(0xffffffffu, o_lane, row) + 4 * sl;
-            ad[k] = (p.add32 && ((vmask >> row) & 1u)) ? __ldg(reinterpret_cast<const float4*>(p.add32 + o[k]))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            ad[k] = (p.add32 && col_ok && ((vmask >> row) & 1u)) ? __ldg(reinterpret_cast<const float4*>(p.add32 + o[k]))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int row = (lane >> 2) + 8 * k;
-            if (!((vmask >> row) & 1u)) continue;
+            if (!((vmask >> row) & 1u) || !col_ok) continue;
             const float4 a4 = *reinterpret_cast<const float4*>(T + row * 16 + ((sl ^ ((row >> 1) & 3)) << 2));
             float t[4] = {fmaf(a4.x, p.acc_scale, sh.x), fmaf(a4.y, p.acc_scale, sh.y), fmaf(a4.z, p.acc_scale, sh.z),
                           fmaf(a4.w, p.acc_scale, sh.w)};
@@ -333,8 +340,10 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           if (p.add32 && p.add_first) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(p.add32 + o_lane) + j4);
-              v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+              if (4 * j4 < nvalid) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.add32 + o_lane) + j4);
+                v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+              }
             }
           }
           if (p.relu == 1) {
@@ -347,14 +356,17 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           if (p.add32 && !p.add_first) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(p.add32 + o_lane) + j4);
-              v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+              if (4 * j4 < nvalid) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.add32 + o_lane) + j4);
+                v[4 * j4] += t.x; v[4 * j4 + 1] += t.y; v[4 * j4 + 2] += t.z; v[4 * j4 + 3] += t.w;
+              }
             }
           }
           if (p.y32) {
             float4* d4 = reinterpret_cast<float4*>(p.y32 + o_lane);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j)
+              if (4 * j < nvalid) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           // split two channels at a time (one packed fp32 -> fp16x2 conversion each way); the range check is one running
           // max instead of a compare per element
@@ -374,8 +386,10 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o_lane);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            dh[j] = reinterpret_cast<const uint4*>(hi)[j];
-            dl[j] = reinterpret_cast<const uint4*>(lo)[j];
+            if (8 * j < nvalid) {
+              dh[j] = reinterpret_cast<const uint4*>(hi)[j];
+              dl[j] = reinterpret_cast<const uint4*>(lo)[j];
+            }
           }
         }
       }

@@ -1124,22 +1124,32 @@ int pack_gen(dd_engine* e, GenLayer& L, const std::string& wkey, const std::stri
   L.cout = transposed ? 4 * cout_conv : cout_conv;
   L.shuffle = transposed ? 1 : 0;
   L.relu = 1;
-  L.nt = (L.cout % 256 == 0) ? 256 : (L.cout % 192 == 0 ? 192 : (L.cout % 128 == 0 ? 128 : 64));
-  if (L.cout % L.nt != 0 || cp % dd::GEN_BK != 0) return fail(DD_ERR_UNSUPPORTED, "producer conv channels not tileable: " + wkey);
+  // N tile: the width in {256, 192, 128} that wastes the fewest padded columns (ties -> wider); 64 for cout <= 64.
+  // A last tile wider than the remaining channels reads zero weight rows (TMA out-of-bounds fill), the epilogue drops them.
+  L.nt = 64;
+  if (L.cout > 64) {
+    int best = 1 << 30;
+    for (int nt : {256, 192, 128}) {
+      const int padded = (L.cout + nt - 1) / nt * nt;
+      if (padded < best) { best = padded; L.nt = nt; }
+    }
+  }
+  if (L.cout % 8 != 0 || cp % 8 != 0) return fail(DD_ERR_UNSUPPORTED, "producer conv channels must be multiples of 8: " + wkey);
+  const int cout_pad = (L.cout + L.nt - 1) / L.nt * L.nt;
   const size_t n = static_cast<size_t>(L.cout) * cp * L.taps;
   float *d_scale = nullptr;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_hi), n * 2))) return rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w_lo), n * 2))) return rc;
-  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.shift), L.cout * 4))) return rc;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.shift), cout_pad * 4))) return rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&d_scale), cout_conv * 4))) return rc;
   if (cp != cin) {
     CUDA_TRY(cudaMemsetAsync(L.w_hi, 0, n * 2, st));
     CUDA_TRY(cudaMemsetAsync(L.w_lo, 0, n * 2, st));
   }
   CUDA_TRY(cudaMemcpyAsync(d_scale, scale.data(), cout_conv * 4, cudaMemcpyHostToDevice, st));
-  std::vector<float> shift_full(L.cout);
+  std::vector<float> shift_full(cout_pad, 0.f);
   for (int i = 0; i < L.cout; ++i) shift_full[i] = shift[i % cout_conv];
-  CUDA_TRY(cudaMemcpyAsync(L.shift, shift_full.data(), L.cout * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(L.shift, shift_full.data(), cout_pad * 4, cudaMemcpyHostToDevice, st));
   const int nraw = static_cast<int>(static_cast<size_t>(cout_conv) * cin * (transposed ? 4 : taps));
   CUDA_TRY(cudaMemsetAsync(scratch, 0, 4, st));
   dd::absmax_scaled_kernel<<<absmax_grid(nraw), 256, 0, st>>>(w->ptr, d_scale, nraw, cin * taps, cout_conv, transposed ? 1 : 0, scratch);
@@ -1235,9 +1245,10 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   a.tiles_x = (W + dd::TILE_W - 1) / dd::TILE_W;
   a.tiles_y = (H + dd::TILE_H - 1) / dd::TILE_H;
   a.m_tiles = a.tiles_x * a.tiles_y * B;
-  a.n_tiles = L.cout / L.nt;
-  a.kc0 = c0 / dd::GEN_BK;
-  a.kc1 = c1 / dd::GEN_BK;
+  a.n_tiles = (L.cout + L.nt - 1) / L.nt;
+  a.kc0 = (c0 + dd::GEN_BK - 1) / dd::GEN_BK;  // a partial last chunk is zero-filled by TMA on both operands
+  a.kc1 = (c1 + dd::GEN_BK - 1) / dd::GEN_BK;
+  a.c0_ch = c0;
   a.taps = L.taps;
   a.cout = L.cout;
   a.shift = L.shift;
@@ -1480,6 +1491,7 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   a.n_tiles = G.N / nt;
   a.kc0 = G.K / dd::GEN_BK;
   a.kc1 = 0;
+  a.c0_ch = G.K;
   a.taps = 1;
   a.cout = G.N;
   a.shift = G.bias;
@@ -1555,9 +1567,9 @@ int run_swin(dd_engine* e, const float* rgb, float* const* feats_out, cudaStream
       aa.status = e->status;
       if ((e->cfg.flags & DD_FLAG_SIMT_CONV) || (nH & 1) || e->attn_simt) {  // fp32 CUDA-core check path
         dd::window_attention_kernel<<<B * aa.nWx * aa.nWy * nH, 64, 0, st>>>(aa);
-      } else {  // tcgen05: pairs of heads of one window per M = 128 tile, four persistent CTAs per SM
+      } else {  // tcgen05: pairs of heads of one window per M = 128 tile, three persistent CTAs per SM
         const int pairs = B * aa.nWx * aa.nWy * (nH / 2);
-        const int grid = pairs < 4 * e->sm_count ? pairs : 4 * e->sm_count;
+        const int grid = pairs < 3 * e->sm_count ? pairs : 3 * e->sm_count;
         dd::window_attention_umma_kernel<<<grid, 128, dd::WAU_SMEM, st>>>(aa, pairs);
       }
       e->launches++;
@@ -1950,8 +1962,8 @@ int dd_enable_producers(dd_handle h, const dd_producer_config* pc) {
     p.C[i] = pc->channels[i];
     p.H[i] = pc->heights[i];
     p.W[i] = pc->widths[i];
-    if (p.C[i] % dd::GEN_BK != 0 || p.C[i] <= 0) return fail(DD_ERR_UNSUPPORTED, "feature channels must be multiples of 64");
-    if (p.neck && p.C[i] % 192 != 0) return fail(DD_ERR_UNSUPPORTED, "neck channel counts must tile by 192");
+    // 16-byte rows for TMA and the vector stores of the epilogues; nothing else constrains the counts (MPViT: 128/216/288/288)
+    if (p.C[i] % 8 != 0 || p.C[i] <= 0) return fail(DD_ERR_UNSUPPORTED, "feature channels must be positive multiples of 8");
     // the FPN's adaptive_avg_pool2d (reference head :121) is the identity only for exact 2x pyramids; otherwise the
     // ConvT output (2x the coarser level) is average-pooled down to the lateral's size by a dedicated kernel
     if (i > 0 && (p.H[i - 1] != 2 * p.H[i] || p.W[i - 1] != 2 * p.W[i])) {

@@ -331,10 +331,11 @@ __global__ void __launch_bounds__(64) window_attention_kernel(const AttnArgs a) 
 //   O        D_O[u] (TMEM columns 32 u .., over S) = P V_u: 3 passes x 4 K-steps, M = 128, N = 32;
 //   store    each thread loads its 32 outputs, splits them and writes the proj GEMM's input planes.
 // 36 small MMAs per pair (~105 cycles each: N <= 64 is floor-bound) against ~2 x 3.1 k SM cycles of fp32 FMAs in the
-// SIMT kernel; four CTAs per SM overlap one's softmax with the others' gathers and MMAs.  Replaces reference swin.py:150-189 / 250-325.
+// SIMT kernel; three CTAs per SM overlap one's softmax with the others' gathers and MMAs.  Replaces reference swin.py:150-189 / 250-325.
 // P re-uses the Q / K tiles (they are dead once the S MMAs have completed) and O re-uses the S columns of TMEM (every row of S is
-// in registers by then): 50 KB of shared memory, 128 TMEM columns and 128 registers per thread, so FOUR CTAs fit an SM (all 512 TMEM
-// columns, 200 KB of shared memory): the phases of a pair are serialised inside a CTA, the overlap comes from its neighbours.
+// in registers by then): 50 KB of shared memory and 128 TMEM columns per CTA, so three CTAs fit an SM at 168 registers per thread
+// (measured: 2 CTAs 2.59 ms, 3 CTAs 2.08 ms, 4 CTAs at 128 registers 2.28 ms per 4 maps): the phases of a pair are serialised
+// inside a CTA, the overlap comes from its neighbours.
 constexpr int WAU_SMEM = 32768 /*Q + K, then P*/ + 16384 /*Vt*/ + 1024 /*align*/ + 1024 /*ctrl*/;
 __device__ __forceinline__ void wau_split8(const float* v, float scale, uint4& hi, uint4& lo, bool& ov) {
   __align__(16) __half2 h[4];
@@ -352,7 +353,7 @@ __device__ __forceinline__ void wau_split8(const float* v, float scale, uint4& h
   hi = *reinterpret_cast<const uint4*>(h);
   lo = *reinterpret_cast<const uint4*>(l);
 }
-__global__ void __launch_bounds__(128, 4) window_attention_umma_kernel(const AttnArgs a, int num_pairs) {
+__global__ void __launch_bounds__(128, 3) window_attention_umma_kernel(const AttnArgs a, int num_pairs) {
   constexpr int WS = 7, N = 49, D = 32;
   constexpr float kP = 4096.f;  // probabilities are split at this scale
   extern __shared__ uint8_t wau_raw[];

@@ -197,7 +197,7 @@ class DDIMHeadBase(nn.Module):
 
     @classmethod
     def _pyramid_ok(cls, feats):
-        return cls._sizes_ok([tuple(f.shape[-2:]) for f in feats]) and all(f.shape[1] % 64 == 0 for f in feats)  # the engine's K chunk (convgen.cuh GEN_BK)
+        return cls._sizes_ok([tuple(f.shape[-2:]) for f in feats]) and all(f.shape[1] % 8 == 0 for f in feats)  # 16-byte NHWC rows (TMA)
 
     def attach_backbone(self, backbone):
         self.__dict__['_backbone_ref'] = weakref.ref(backbone)

@@ -3,8 +3,9 @@ src/model/head/ddim_depth_estimate_res_mpvit_HAHI.py:16-185): HAHI neck + FPN ov
 1/2 .. 1/16 of the image, the Swin heads' denoiser (upsample_fuse = bilinear(align_corners) + convA/convB; with the
 condition map already at latent resolution the resize is the identity).
 
-The loop + decoder run on the engine like every other head.  216 and 288 are not multiples of the tensor-core
-path's 32-channel K chunk, so neck + FPN of this head take the fallback producer path (torch ops, TF32 off)."""
+Neck, FPN, loop and decoder run on the engine like every other head: 216 and 288 are not multiples of the
+tensor-core conv's 64-channel K chunk or of its N tiles, the partial chunks / tiles are completed with zeros by TMA's
+out-of-bounds fill (convgen.cuh).  Only the MPViT backbone itself stays a torch module."""
 from ..necks.hahi import HAHIHeteroNeck
 from ..registry import HEADS
 from ._ddim_head import DDIMHeadBase

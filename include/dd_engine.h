@@ -119,8 +119,10 @@ int dd_set_schedule(dd_handle h, const int64_t* timesteps, const double* c_x, co
 /* Optional: also run the step-invariant condition producers natively — HAHI neck (attention gates off, as
  * the shipped heads configure it: src/model/necks/hahi.py:165-276) and the FPN (head :112-122) — on the same
  * 3-pass tensor-core path.  Call before dd_finalize_weights; additionally register the reference keys
- * `hahineck.*` (only if has_neck), `conv_lateral.*`, `conv_up.*`.  Needs an exact 2x feature pyramid (the
- * FPN's adaptive_avg_pool2d is then the identity) and channel counts that are multiples of 32. */
+ * `hahineck.*` (only if has_neck), `conv_lateral.*`, `conv_up.*`.  Pyramid levels may be anything up to 2x their
+ * coarser neighbour (an exact 2x pyramid makes the FPN's adaptive_avg_pool2d the identity; otherwise it is a real
+ * resample kernel).  Channel counts: any positive multiples of 8 (Swin 192..1536, ResNet 64..512, MPViT 128/216/288/288);
+ * partial 64-channel K chunks and partial N tiles are completed with zeros by TMA's out-of-bounds fill. */
 typedef struct dd_producer_config {
   int32_t num_levels;   /* 2..4 */
   int32_t channels[4];  /* backbone feature channels, finest level first */

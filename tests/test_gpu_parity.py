@@ -29,6 +29,14 @@ def _res_head(steps, seed=7):
                             num_train_timesteps=1000, depth_feature_dim=16, loss_cfgs=[], init_cfg=None)).eval()
 
 
+def _mpvit_head(steps, seed=7):
+    from diffusiondepth_b200.model.registry import HEADS
+    torch.manual_seed(seed)
+    return HEADS.build(dict(type="DDIMDepthEstimate_MPVIT_ADDHAHI", in_channels=[64, 128, 256, 512],
+                            inference_steps=steps, num_train_timesteps=1000, depth_feature_dim=16, loss_cfgs=[],
+                            init_cfg=None)).eval()
+
+
 def _head_sd(head):
     return {"depth_head." + k: v.detach().cpu() for k, v in head.state_dict().items()}
 
@@ -171,11 +179,14 @@ def test_loop_and_decode_vs_oracle(variant, hw, T):
 
 
 # ------------------------------------------------------------------------------------------------ producers
-@pytest.mark.parametrize("variant,hw0", [("swin", (16, 32)), ("swin", (24, 40)), ("res", (32, 48))])
+@pytest.mark.parametrize("variant,hw0", [("swin", (16, 32)), ("swin", (24, 40)), ("res", (32, 48)), ("mpvit", (32, 48)),
+                                         ("mpvit", (24, 40))])
 def test_native_neck_and_fpn_vs_oracle(variant, hw0):
     """dd_build_condition (HAHI neck + FPN on the tensor-core conv path, BN folded, concat-free) vs the fp64
-    restatement of reference necks/hahi.py:165-276 + head :112-122, and vs the mirror's torch-op producers."""
-    head = (_res_head if variant == "res" else _swin_head)(2).to(DEV)
+    restatement of reference necks/hahi.py:165-276 + head :112-122, and vs the mirror's torch-op producers.
+    mpvit: channels 128/216/288/288 — partial 64-channel K chunks (216 = 3.375 x 64, the second concat source starting
+    at weight column 216) and partial N tiles (216 of 256, 288 of 2 x 192), completed by TMA out-of-bounds zero fill."""
+    head = {"res": _res_head, "swin": _swin_head, "mpvit": _mpvit_head}[variant](2).to(DEV)
     with torch.no_grad():  # make BN non-trivial
         for m in head.modules():
             if isinstance(m, torch.nn.BatchNorm2d):
@@ -184,16 +195,17 @@ def test_native_neck_and_fpn_vs_oracle(variant, hw0):
                 m.weight.uniform_(0.5, 1.5)
                 m.bias.normal_(0, 0.2)
     sd = _head_sd(head)
-    chans = (192, 384, 768, 1536) if variant == "swin" else (64, 128, 256, 512)
+    chans = {"swin": (192, 384, 768, 1536), "res": (64, 128, 256, 512), "mpvit": (128, 216, 288, 288)}[variant]
     g = torch.Generator().manual_seed(11)
     feats = [torch.randn(2, c, hw0[0] >> i, hw0[1] >> i, generator=g) for i, c in enumerate(chans)]
     fd = [f.to(DEV) for f in feats]
     lat = (2 * hw0[0], 2 * hw0[1]) if variant == "swin" else hw0
+    assert head._pyramid_ok(fd)
     eng = head._engine(2, lat, hw0, DEV, feats=fd)
     cond = eng.build_condition(fd, want_cond=True)
     eng.poll_status()
     f64 = [f.double() for f in feats]
-    ref = restate.fpn_condition(sd, restate.hahi_neck(sd, f64) if variant == "swin" else f64)
+    ref = restate.fpn_condition(sd, restate.hahi_neck(sd, f64) if variant != "res" else f64)
     err = (cond.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 5e-5, err
     from diffusiondepth_b200.model._blocks import exact_fp32
@@ -290,7 +302,7 @@ def test_producers_reject_unsupported_pyramids():
     with pytest.raises(dd.EngineError, match="DD_ERR_UNSUPPORTED"):
         eng.enable_producers([64, 128, 256, 512], [(32, 48), (10, 19), (5, 10), (3, 5)], has_neck=False)  # > 2x jump
     with pytest.raises(dd.EngineError, match="DD_ERR_UNSUPPORTED"):
-        eng.enable_producers([60, 128, 256, 512], [(32, 48), (16, 24), (8, 12), (4, 6)], has_neck=False)  # 60 % 32 != 0
+        eng.enable_producers([60, 128, 256, 512], [(32, 48), (16, 24), (8, 12), (4, 6)], has_neck=False)  # 60 % 8 != 0
 
 
 # ------------------------------------------------------------------------------------------------ whole plugin
@@ -318,6 +330,8 @@ def test_plugin_forward_matches_reference_golden(case, parity_log):
     """`Diffusion_DCbase_Model.forward(sample)` on the GPU vs the real reference's own forward (golden).  `*_trained`:
     the trained-like regime (non-zero Swin relative-position tables, non-trivial BN statistics, LN / GN affines)."""
     g, m, out = _run_plugin(case)
+    assert all(e.producers is not None for e in m.depth_head._engines.values()), \
+        "neck + FPN must run on the engine for every family"
     z = m.depth_head.last_logits.cpu()
     z_ref = torch.from_numpy(g["z"]["logits"])
     dz = (helpers.golden_view(g, "logits", z) - z_ref).abs()
