@@ -19,10 +19,13 @@ struct GenConvArgs {
                       // with zeros by TMA's out-of-bounds fill, on the activation AND the weight side)
   int c0_ch;          // real channel count of source 0 = weight K offset of source 1's first channel
   int taps;           // 1 (1x1) or 9 (3x3, pad 1)
+  int ld_out, ch_off; // output rows are ld_out channels wide and this layer writes [ch_off, ch_off + cout) of them: branches
+                      // of a concatenation write straight into the concatenated tensor (ld_out = cout, ch_off = 0 otherwise;
+                      // not combined with `shuffle`).  The residual `add32` is always dense [pixel][cout].
   int cout;           // total output channels (any multiple of 8; n_tiles = ceil(cout / NT), columns >= cout are dropped)
   const float* shift; // [cout] bias / folded BN shift
   float acc_scale;
-  int relu;           // activation: 0 none, 1 ReLU, 2 exact (erf) GELU
+  int relu;           // activation: 0 none, 1 ReLU, 2 exact (erf) GELU, 3 Hardswish x * relu6(x + 3) / 6
   int m_valid;        // > 0: GEMM mode (B = 1, W = 16): only "pixels" (tokens) with index < m_valid are stored
   int stride;         // 1 or 2: input pixel of output (y, x), tap (dy, dx) is (stride*y + dy, stride*x + dx); the A tensor
                       // maps are then built with elementStrides = stride so one box still delivers 8 x 16 pixels
@@ -268,6 +271,7 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
       // element offset of this lane's row at channel 0 (non-shuffle) -- fits 32 bits for every tensor we produce
       const uint32_t row_base = static_cast<uint32_t>(((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.cout);
+      const uint32_t row_out = static_cast<uint32_t>(((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.ld_out + p.ch_off);
       mbar_wait(&tfull_bar[buf], (full_phase >> buf) & 1u);
       full_phase ^= (1u << buf);
       tc_fence_after();
@@ -288,6 +292,7 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
         } else {
           o_lane = row_base + static_cast<uint32_t>(n0);
         }
+        const uint32_t o_out = p.shuffle ? o_lane : row_out + static_cast<uint32_t>(n0);  // where the outputs go
         if (xpose_path) {
           // row `lane`, float4 slot s -> T[lane][s ^ ((lane >> 1) & 3)]: conflict-free 16-byte writes and reads
 #pragma unroll
@@ -299,12 +304,13 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           const int sl = lane & 3;  // this lane's float4 slot: channels n0 + 4 sl .. + 3
           const bool col_ok = 4 * sl < nvalid;
           const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0) + sl);  // shift[] is padded to n_tiles * NT
-          uint32_t o[4];
+          uint32_t o[4], oo[4];
           float4 ad[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {  // rows (lane >> 2) + 8 k: issue the addend loads before any store
             const int row = (lane >> 2) + 8 * k;
             o[k] = __shfl_sync(0xffffffffu, o_lane, row) + 4 * sl;
+            oo[k] = __shfl_sync(0xffffffffu, o_out, row) + 4 * sl;
             ad[k] = (p.add32 && col_ok && ((vmask >> row) & 1u)) ? __ldg(reinterpret_cast<const float4*>(p.add32 + o[k]))
                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -321,9 +327,10 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
               if (p.add_first) t[j] += av[j];
               if (p.relu == 1) t[j] = fmaxf(t[j], 0.f);
               else if (p.relu == 2) t[j] = 0.5f * t[j] * (1.f + erff(t[j] * 0.70710678118654752f));
+              else if (p.relu == 3) t[j] = t[j] * fminf(fmaxf(t[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
               if (!p.add_first) t[j] += av[j];
             }
-            if (p.y32) *reinterpret_cast<float4*>(p.y32 + o[k]) = make_float4(t[0], t[1], t[2], t[3]);
+            if (p.y32) *reinterpret_cast<float4*>(p.y32 + oo[k]) = make_float4(t[0], t[1], t[2], t[3]);
           }
           __syncwarp();
         } else if (valid) {
@@ -352,6 +359,9 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
           } else if (p.relu == 2) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+          } else if (p.relu == 3) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] * fminf(fmaxf(v[j] + 3.f, 0.f), 6.f) * (1.f / 6.f);
           }
           if (p.add32 && !p.add_first) {
 #pragma unroll
@@ -363,7 +373,7 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
             }
           }
           if (p.y32) {
-            float4* d4 = reinterpret_cast<float4*>(p.y32 + o_lane);
+            float4* d4 = reinterpret_cast<float4*>(p.y32 + o_out);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (4 * j < nvalid) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -382,8 +392,8 @@ convgen_umma_kernel(const __grid_constant__ CUtensorMap tmA0_hi, const __grid_co
             lo[j] = __floats2half2_rn(s0 - back.x, s1 - back.y);
           }
           overflow |= !(amax <= 60000.f);  // also catches NaN
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o_lane);
-          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o_lane);
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o_out);
+          uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o_out);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             if (8 * j < nvalid) {

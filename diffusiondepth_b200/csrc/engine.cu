@@ -19,6 +19,7 @@
 #include "conv_halo.cuh"
 #include "conv_swap.cuh"
 #include "swin.cuh"
+#include "mpvit.cuh"
 
 namespace {
 
@@ -203,6 +204,9 @@ cudaError_t configure_all_kernels() {
                                 dd::WAU_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dd::decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dd::DEC_SMEM)) != cudaSuccess)
     return e;
+  // k^T v of one image (8 heads x Ch^2, Ch <= 64) + a 32-token tile of q (C <= 512)
+  if ((e = cudaFuncSetAttribute(dd::factor_att_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (8 * dd::KTV_CH_MAX * dd::KTV_CH_MAX + dd::FA_T * 512) * 4)) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<16, 64, 16>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<64, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<256, 256, 32>()) != cudaSuccess) return e;
@@ -445,6 +449,45 @@ struct ResNetW {
   float* D32 = nullptr;
 };
 
+// MPViT (reference backbone/mpvit.py): depthwise layers as tap-major fp32 tables, every 1x1 conv / Linear on the GEMM path
+struct DwLayer {
+  int C = 0, K = 3;
+  float* w = nullptr;     // [K*K][C], eval-BN scale folded in
+  float* bias = nullptr;  // [C]
+};
+struct MpBlockW {
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  Gemm qkv, proj, fc1, fc2;
+};
+struct MpEncoderW {
+  DwLayer cpe;              // ConvPosEnc, shared by the encoder's layers
+  float* crpe_w = nullptr;  // [49][C]: the 3 / 5 / 7 windows of the head groups, centred in one 7 x 7 layout
+  float* crpe_b = nullptr;
+  std::vector<MpBlockW> layers;
+};
+struct MpStageW {
+  DwLayer pe_dw[4], inv_dw;
+  GenLayer pe_pw[4], inv1, inv2, agg;
+  MpEncoderW enc[4];
+};
+struct MPViTW {
+  bool enabled = false, ready = false;
+  int H = 0, W = 0, heads = 8, mlp_ratio = 4;
+  int dims[4] = {0, 0, 0, 0}, out_dims[4] = {0, 0, 0, 0}, layers[4] = {0, 0, 0, 0}, paths[4] = {0, 0, 0, 0};
+  int Hs[4] = {0, 0, 0, 0}, Ws[4] = {0, 0, 0, 0};
+  int radius[16] = {0};     // crpe window / 2 per head ({3: 2, 5: 3, 7: 3} heads)
+  GenLayer stem0, stem1;
+  MpStageW stage[4];
+  // workspace views
+  Planes IN, S1, D, EP0, AP, HP, CAT;
+  float* XS = nullptr;      // stem output, then each stage's output (fp32 NHWC)
+  float* E[4] = {nullptr, nullptr, nullptr, nullptr};  // the paths' token maps + one swap buffer
+  float* R1 = nullptr;
+  float* QKV = nullptr;
+  float *part_m = nullptr, *part_s = nullptr, *colmax = nullptr, *colinv = nullptr, *part_ktv = nullptr, *ktv = nullptr;
+};
+constexpr int kMpChunksMax = 128;  // token chunks of the factorised attention's reductions
+
 }  // namespace
 
 struct dd_engine {
@@ -484,6 +527,7 @@ struct dd_engine {
   Producers prod;
   Backbone bb;
   ResNetW rn;
+  MPViTW mp;
   bool feats_ready = false;  // dd_run_backbone has filled the neck's input planes
   bool cond_ready = false;  // dd_build_condition has filled `cond` for the next dd_denoise_decode(cond = NULL)
   // CUDA graphs (DD_FLAG_CUDA_GRAPH), captured on first use and replayed: the T-step loop, the same loop with a decode
@@ -595,8 +639,9 @@ size_t carve(dd_engine* e, void* base) {
   v->temb_sel = c.take<float>(static_cast<size_t>(g.B) * 256);
   if (e->cfg.flags & DD_FLAG_STEP_DECODE)
     v->inter = c.take<float>(static_cast<size_t>(e->cfg.num_inference_steps) * BP * 4);
-  if (e->rn.enabled || e->bb.enabled)
-    v->rgb_stage = c.take<float>(static_cast<size_t>(g.B) * 3 * (e->rn.enabled ? e->rn.H * e->rn.W : e->bb.H * e->bb.W));
+  if (e->rn.enabled || e->bb.enabled || e->mp.enabled)
+    v->rgb_stage = c.take<float>(static_cast<size_t>(g.B) * 3 *
+                                 (e->rn.enabled ? e->rn.H * e->rn.W : (e->mp.enabled ? e->mp.H * e->mp.W : e->bb.H * e->bb.W)));
   if (e->prod.enabled) {
     const Producers& pc = e->prod;
     Producers* pv = &v->prod;
@@ -648,6 +693,42 @@ size_t carve(dd_engine* e, void* base) {
     bv->AP.lo = c.take<__half>(m0 * c0);
     bv->HP.hi = c.take<__half>(m0 * c0 * 4);
     bv->HP.lo = c.take<__half>(m0 * c0 * 4);
+  }
+  if (e->mp.enabled) {
+    const MPViTW& mc = e->mp;
+    MPViTW* mv = &v->mp;
+    const size_t pin = static_cast<size_t>(g.B) * mc.H * mc.W;
+    size_t tok = 0, cat = 0, xs = pin * mc.dims[0];
+    int cmax = 0;
+    for (int s = 0; s < 4; ++s) {
+      const size_t M = static_cast<size_t>(g.B) * mc.Hs[s] * mc.Ws[s] + 256;  // slack: the GEMM's token "image" is 16 wide
+      tok = std::max(tok, M * mc.dims[s]);
+      cat = std::max(cat, M * mc.dims[s] * (mc.paths[s] + 1));
+      xs = std::max(xs, M * mc.out_dims[s]);
+      cmax = std::max(cmax, mc.dims[s]);
+    }
+    auto planes = [&](Planes& pl, size_t n) {
+      pl.hi = c.take<__half>(n);
+      pl.lo = c.take<__half>(n);
+    };
+    planes(mv->IN, pin * dd::GEN_BK);
+    planes(mv->S1, pin * (mc.dims[0] / 2));
+    mv->XS = c.take<float>(xs);
+    for (int i = 0; i < 4; ++i) mv->E[i] = c.take<float>(tok);
+    mv->R1 = c.take<float>(tok);
+    mv->QKV = c.take<float>(tok * 3);
+    planes(mv->D, tok);
+    planes(mv->EP0, tok);
+    planes(mv->AP, tok);
+    planes(mv->HP, tok * mc.mlp_ratio);
+    planes(mv->CAT, cat);
+    const size_t chm = static_cast<size_t>(cmax / mc.heads), nk = static_cast<size_t>(mc.heads) * chm * chm;
+    mv->part_m = c.take<float>(static_cast<size_t>(g.B) * kMpChunksMax * cmax);
+    mv->part_s = c.take<float>(static_cast<size_t>(g.B) * kMpChunksMax * cmax);
+    mv->colmax = c.take<float>(static_cast<size_t>(g.B) * cmax);
+    mv->colinv = c.take<float>(static_cast<size_t>(g.B) * cmax);
+    mv->part_ktv = c.take<float>(static_cast<size_t>(g.B) * kMpChunksMax * nk);
+    mv->ktv = c.take<float>(static_cast<size_t>(g.B) * nk);
   }
   return align_up(c.off, 1024);
 }
@@ -1236,7 +1317,8 @@ cudaError_t launch_gen_nt(int nt, bool pair, int grid, cudaStream_t st, const CU
 
 // H, W: OUTPUT grid.  With L.stride == 2 the sources live on a (src_h, src_w) grid.
 int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Planes& a1, int c1, int H, int W,
-            float* y32, const float* add32, const Planes* out, cudaStream_t st, int src_h = 0, int src_w = 0) {
+            float* y32, const float* add32, const Planes* out, cudaStream_t st, int src_h = 0, int src_w = 0,
+            int ld_out = 0, int ch_off = 0) {
   const int B = e->cfg.batch;
   dd::GenConvArgs a;
   a.B = B;
@@ -1251,6 +1333,8 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   a.c0_ch = c0;
   a.taps = L.taps;
   a.cout = L.cout;
+  a.ld_out = ld_out > 0 ? ld_out : L.cout;  // branches of a concatenation write straight into the concatenated planes
+  a.ch_off = ch_off;
   a.shift = L.shift;
   a.acc_scale = 1.f / (kProdScale * L.wscale);
   a.relu = L.relu;
@@ -1392,19 +1476,28 @@ int pack_gemm(dd_engine* e, Gemm& G, const std::string& wkey, const std::string&
   if (w->shape != std::vector<int64_t>{N, K}) return fail(DD_ERR_INVALID, "weight shape mismatch: " + wkey);
   G.K = K;
   G.N = N;
-  G.nt = (N % 256 == 0) ? 256 : 192;
-  if (N % G.nt != 0 || K % dd::GEN_BK != 0) return fail(DD_ERR_UNSUPPORTED, "linear layer not tileable: " + wkey);
+  // N tile as in pack_gen: fewest padded columns among {256, 192, 128}, 64 for N <= 64; partial K chunks / N tiles are
+  // completed with zeros by TMA (Swin-L: every N is a multiple of 256 or 192, every K of 64; MPViT: 216, 288, 648, 864 ...)
+  G.nt = 64;
+  if (N > 64) {
+    int best = 1 << 30;
+    for (int nt : {256, 192, 128}) {
+      const int padded = (N + nt - 1) / nt * nt;
+      if (padded < best) { best = padded; G.nt = nt; }
+    }
+  }
+  if (N % 8 != 0 || K % 8 != 0) return fail(DD_ERR_UNSUPPORTED, "linear layer widths must be multiples of 8: " + wkey);
+  const int n_pad = (N + G.nt - 1) / G.nt * G.nt;
   const size_t n = static_cast<size_t>(N) * K;
   int rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&G.w_hi), n * 2))) return rc;
   if ((rc = dev_alloc(e, reinterpret_cast<void**>(&G.w_lo), n * 2))) return rc;
-  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&G.bias), N * 4))) return rc;
+  if ((rc = dev_alloc(e, reinterpret_cast<void**>(&G.bias), n_pad * 4))) return rc;
+  CUDA_TRY(cudaMemsetAsync(G.bias, 0, n_pad * 4, st));
   if (!bkey.empty()) {
     const Raw* b = find(e, bkey);
     if (!b) return fail(DD_ERR_INVALID, "missing weights: " + bkey);
     CUDA_TRY(cudaMemcpyAsync(G.bias, b->ptr, N * 4, cudaMemcpyDeviceToDevice, st));
-  } else {
-    CUDA_TRY(cudaMemsetAsync(G.bias, 0, N * 4, st));
   }
   CUDA_TRY(cudaMemsetAsync(scratch, 0, 4, st));
   dd::absmax_kernel<<<absmax_grid(n), 256, 0, st>>>(w->ptr, static_cast<int>(n), scratch);
@@ -1418,7 +1511,7 @@ int pack_gemm(dd_engine* e, Gemm& G, const std::string& wkey, const std::string&
   if ((rc = make_wgen_map(&G.mb_lo, G.w_lo, N, K, 1, G.nt))) return rc;
   if ((rc = make_wgen_map(&G.mp_hi, G.w_hi, N, K, 1, G.nt / 2))) return rc;
   if ((rc = make_wgen_map(&G.mp_lo, G.w_lo, N, K, 1, G.nt / 2))) return rc;
-  G.alt = (G.nt == 256 && N % 192 == 0);
+  G.alt = (G.nt == 256 && N % 256 == 0 && N % 192 == 0);
   if (G.alt) {
     if ((rc = make_wgen_map(&G.mb_hi_alt, G.w_hi, N, K, 1, 192))) return rc;
     if ((rc = make_wgen_map(&G.mb_lo_alt, G.w_lo, N, K, 1, 192))) return rc;
@@ -1470,7 +1563,7 @@ int pack_backbone(dd_engine* e, cudaStream_t st, float* scratch) {
 
 // y = act(A[M][K] @ W^T + bias) (+ add32): tokens are laid out as a [ceil(M/16)][16] "image" for the conv kernel
 int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float* y32, const float* add32,
-             const Planes* out, cudaStream_t st) {
+             const Planes* out, cudaStream_t st, int ld_out = 0, int ch_off = 0) {
   dd::GenConvArgs a;
   a.B = 1;
   a.W = 16;
@@ -1488,12 +1581,14 @@ int run_gemm(dd_engine* e, const Gemm& G, const Planes& A, int M, int act, float
   }
   const CUtensorMap& mbh = pair ? ((nt == G.nt) ? G.mp_hi : G.mp_hi_alt) : ((nt == G.nt) ? G.mb_hi : G.mb_hi_alt);
   const CUtensorMap& mbl = pair ? ((nt == G.nt) ? G.mp_lo : G.mp_lo_alt) : ((nt == G.nt) ? G.mb_lo : G.mb_lo_alt);
-  a.n_tiles = G.N / nt;
-  a.kc0 = G.K / dd::GEN_BK;
+  a.n_tiles = (G.N + nt - 1) / nt;
+  a.kc0 = (G.K + dd::GEN_BK - 1) / dd::GEN_BK;
   a.kc1 = 0;
   a.c0_ch = G.K;
   a.taps = 1;
   a.cout = G.N;
+  a.ld_out = ld_out > 0 ? ld_out : G.N;
+  a.ch_off = ch_off;
   a.shift = G.bias;
   a.acc_scale = 1.f / (kTokScale * G.wscale);
   a.relu = act;
@@ -1599,6 +1694,8 @@ int run_swin(dd_engine* e, const float* rgb, float* const* feats_out, cudaStream
   }
   return DD_OK;
 }
+
+#include "mpvit_host.inc"
 
 }  // namespace
 
@@ -1806,6 +1903,9 @@ int dd_finalize_weights(dd_handle h, void* cuda_stream) {
   h->rn.ready = false;
   if (h->rn.enabled)
     if ((rc = pack_resnet(h, st, scratch))) return rc;
+  h->mp.ready = false;
+  if (h->mp.enabled)
+    if ((rc = pack_mpvit(h, st, scratch))) return rc;
   // the registered pointers were borrowed for this call only (include/dd_engine.h): forget them, so a later finalize
   // cannot read memory the caller has freed in the meantime — every key has to be registered again
   h->raw.clear();
@@ -2079,8 +2179,47 @@ int dd_enable_backbone(dd_handle h, const dd_backbone_config* bc) {
     }
     h->rn = r;
     h->bb.enabled = false;
+    h->mp.enabled = false;
     h->weights_ready = false;
     h->ws = nullptr;
+    drop_graphs(h);
+    return DD_OK;
+  }
+  if (bc->kind == DD_BACKBONE_MPVIT) {
+    if (!h->prod.enabled || h->prod.nlev != 4)
+      return fail(DD_ERR_INVALID, "dd_enable_producers (4 levels) must be called first");
+    MPViTW m;
+    m.enabled = true;
+    m.H = bc->height;
+    m.W = bc->width;
+    m.heads = 8;  // every MPViT variant (reference mpvit.py:743-870)
+    m.mlp_ratio = bc->mlp_ratio;
+    if (m.mlp_ratio < 1 || m.mlp_ratio > 8) return fail(DD_ERR_INVALID, "bad MPViT mlp_ratio");
+    int hh = bc->height, ww = bc->width;
+    for (int s = 0; s < 4; ++s) {
+      m.dims[s] = bc->mp_dims[s];
+      m.layers[s] = bc->depths[s];
+      m.paths[s] = bc->mp_paths[s];
+      if (m.layers[s] < 1 || m.paths[s] < 1 || m.paths[s] > 3) return fail(DD_ERR_UNSUPPORTED, "MPViT: 1..3 paths, >= 1 layer per stage");
+      if (m.dims[s] <= 0 || m.dims[s] % 8 != 0 || m.dims[s] / m.heads > dd::KTV_CH_MAX || m.dims[s] > 512)
+        return fail(DD_ERR_UNSUPPORTED, "MPViT: stage widths must be multiples of 8 (8 heads), at most 512");
+      hh = (hh - 1) / 2 + 1;  // depthwise 3x3, stride 2, pad 1
+      ww = (ww - 1) / 2 + 1;
+      m.Hs[s] = hh;
+      m.Ws[s] = ww;
+    }
+    if (m.dims[0] % 16 != 0) return fail(DD_ERR_UNSUPPORTED, "MPViT: stem width must be a multiple of 16");
+    for (int s = 0; s < 4; ++s) {
+      m.out_dims[s] = s < 3 ? m.dims[s + 1] : m.dims[s];
+      if (m.Hs[s] != h->prod.H[s] || m.Ws[s] != h->prod.W[s] || m.out_dims[s] != h->prod.C[s])
+        return fail(DD_ERR_INVALID, "backbone stage geometry does not match the producer pyramid");
+    }
+    h->mp = m;
+    h->bb.enabled = false;
+    h->rn.enabled = false;
+    h->weights_ready = false;
+    h->ws = nullptr;
+    drop_graphs(h);
     return DD_OK;
   }
   if (bc->kind != DD_BACKBONE_SWIN) return fail(DD_ERR_UNSUPPORTED, "unknown backbone kind");
@@ -2107,16 +2246,22 @@ int dd_enable_backbone(dd_handle h, const dd_backbone_config* bc) {
     ww = (ww + 1) / 2;
   }
   h->bb = b;
+  h->rn.enabled = false;
+  h->mp.enabled = false;
   h->weights_ready = false;
   h->ws = nullptr;
+  drop_graphs(h);
   return DD_OK;
 }
 
 int dd_run_backbone(dd_handle h, const float* rgb, float* const* feats_out, void* workspace, size_t workspace_bytes,
                     void* cuda_stream) {
   if (!h || !rgb) return fail(DD_ERR_INVALID, "null argument");
-  const bool swin = h->bb.enabled && h->bb.ready, resnet = h->rn.enabled && h->rn.ready;
-  if (!h->weights_ready || !(swin || resnet)) return fail(DD_ERR_INVALID, "backbone not enabled / weights not finalized");
+  const bool swin = h->bb.enabled && h->bb.ready, resnet = h->rn.enabled && h->rn.ready, mpvit = h->mp.enabled && h->mp.ready;
+  if (!h->weights_ready || !(swin || resnet || mpvit)) return fail(DD_ERR_INVALID, "backbone not enabled / weights not finalized");
+  auto run = [&](const float* img, float* const* outs, cudaStream_t s) {
+    return swin ? run_swin(h, img, outs, s) : (resnet ? run_resnet(h, img, outs, s) : run_mpvit(h, img, outs, s));
+  };
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   int rc;
@@ -2127,13 +2272,11 @@ int dd_run_backbone(dd_handle h, const float* rgb, float* const* feats_out, void
   for (int i = 0; feats_out && i < 4; ++i) want_out |= (feats_out[i] != nullptr);
   if ((h->cfg.flags & DD_FLAG_CUDA_GRAPH) && !want_out) {
     // the graph's kernels read the image from the workspace: stage the caller's batch there first (20 MB at C3)
-    const size_t n = static_cast<size_t>(h->cfg.batch) * 3 * (swin ? h->bb.H * h->bb.W : h->rn.H * h->rn.W);
+    const size_t n = static_cast<size_t>(h->cfg.batch) * 3 *
+                     (swin ? h->bb.H * h->bb.W : (resnet ? h->rn.H * h->rn.W : h->mp.H * h->mp.W));
     CUDA_TRY(cudaMemcpyAsync(h->rgb_stage, rgb, n * 4, cudaMemcpyDeviceToDevice, st));
-    if ((rc = graph_run(h, dd_engine::G_BACKBONE, st, [&](cudaStream_t s) {
-           return swin ? run_swin(h, h->rgb_stage, nullptr, s) : run_resnet(h, h->rgb_stage, nullptr, s);
-         })))
-      return rc;
-  } else if ((rc = swin ? run_swin(h, rgb, feats_out, st) : run_resnet(h, rgb, feats_out, st))) {
+    if ((rc = graph_run(h, dd_engine::G_BACKBONE, st, [&](cudaStream_t s) { return run(h->rgb_stage, nullptr, s); }))) return rc;
+  } else if ((rc = run(rgb, feats_out, st))) {
     return rc;
   }
   h->feats_ready = true;

@@ -1,0 +1,318 @@
+// MPViT backbone (reference src/model/backbone/mpvit.py:57-741): the pieces that are not GEMMs.  Every 1x1 conv and Linear
+// of the network runs on convgen_umma_kernel (3-pass fp16 split on tcgen05); what is left is HBM/L2-bound pointwise and
+// stencil work on fp32 NHWC token maps [B, H, W, C]:
+//   dwconv_nhwc_kernel        depthwise k x k (stride 1 / 2), + bias / folded eval-BN, Hardswish, residual (ConvPosEnc),
+//                             fp32 and / or fp16 hi/lo plane outputs                      (:125-175, :241-259, :482-532)
+//   ln_split_generic_kernel   LayerNorm(C) for any C <= 512 -> planes                     (:396-436)
+//   ksoftmax_*                softmax of k over the TOKEN axis: per-chunk online max / sum, ordered combine  (:374)
+//   ktv_*                     k_softmax^T v per (image, head): per-chunk partial [Ch x Ch] sums, ordered combine (:375)
+//   factor_att_apply_kernel   scale * q (k^T v) + q * depthwise_conv_{3,5,7}(v)  -> planes (:376-386, :262-330)
+// All reductions over tokens run in a fixed order (chunk partials, then an ordered combine): results are bit-reproducible.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace dd {
+
+__device__ __forceinline__ float hardswish_f(float v) { return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f); }
+
+// ------------------------------------------------------------------------------------------------ depthwise conv
+struct DwArgs {
+  const float* x;     // fp32 NHWC [B, H, W, C]
+  const float* w;     // [KS*KS][C] tap-major (eval-BN scale folded in)
+  const float* bias;  // [C]: conv bias / folded BN shift (zeros if neither)
+  float* y32;         // nullable: fp32 NHWC [B, Ho, Wo, C]
+  __half* out_hi;     // nullable: fp16 hi/lo planes of split_scale * y
+  __half* out_lo;
+  float split_scale;
+  int B, H, W, C, Ho, Wo, stride;
+  int act;            // 0 none, 3 Hardswish
+  int residual;       // 1: y += x (ConvPosEnc; stride 1 only)
+  int* status;
+};
+
+// one thread = one output pixel x 4 channels (float4 loads along the channel axis are coalesced across the warp)
+template <int KS>
+__global__ void __launch_bounds__(256) dwconv_nhwc_kernel(const DwArgs a) {
+  const int C4 = a.C >> 2;
+  const size_t total = static_cast<size_t>(a.B) * a.Ho * a.Wo * C4;
+  bool ov = false;
+  for (size_t i = blockIdx.x * static_cast<size_t>(256) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * 256) {
+    const int c4 = static_cast<int>(i % C4);
+    const size_t px = i / C4;
+    const int ox = static_cast<int>(px % a.Wo), oy = static_cast<int>((px / a.Wo) % a.Ho);
+    const int b = static_cast<int>(px / (static_cast<size_t>(a.Wo) * a.Ho));
+    float4 acc = __ldg(reinterpret_cast<const float4*>(a.bias) + c4);
+    const int iy0 = oy * a.stride - KS / 2, ix0 = ox * a.stride - KS / 2;
+    const float* img = a.x + static_cast<size_t>(b) * a.H * a.W * a.C;
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+      const int iy = iy0 + ky;
+      if (iy < 0 || iy >= a.H) continue;
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const int ix = ix0 + kx;
+        if (ix < 0 || ix >= a.W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(img + (static_cast<size_t>(iy) * a.W + ix) * a.C) + c4);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.w + (ky * KS + kx) * a.C) + c4);
+        acc.x = fmaf(v.x, w.x, acc.x);
+        acc.y = fmaf(v.y, w.y, acc.y);
+        acc.z = fmaf(v.z, w.z, acc.z);
+        acc.w = fmaf(v.w, w.w, acc.w);
+      }
+    }
+    if (a.residual) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(img + (static_cast<size_t>(oy) * a.W + ox) * a.C) + c4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (a.act == 3) {
+      acc.x = hardswish_f(acc.x); acc.y = hardswish_f(acc.y); acc.z = hardswish_f(acc.z); acc.w = hardswish_f(acc.w);
+    }
+    const size_t o = px * a.C + 4 * c4;
+    if (a.y32) *reinterpret_cast<float4*>(a.y32 + o) = acc;
+    if (a.out_hi) {
+      __half h[4], l[4];
+      split_f16(acc.x, a.split_scale, h[0], l[0], ov);
+      split_f16(acc.y, a.split_scale, h[1], l[1], ov);
+      split_f16(acc.z, a.split_scale, h[2], l[2], ov);
+      split_f16(acc.w, a.split_scale, h[3], l[3], ov);
+      *reinterpret_cast<uint2*>(a.out_hi + o) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(a.out_lo + o) = *reinterpret_cast<const uint2*>(l);
+    }
+  }
+  if (ov) atomicOr(a.status, 1);
+}
+
+// depthwise weights [C][1][K][K] (optionally scaled per channel) -> tap-major [KD*KD][C] at the centre of a KD x KD
+// window (KD >= K; the crpe table holds its 3 / 5 / 7 windows in one 7 x 7 layout), channel offset c0 of C_total
+__global__ void pack_dw_weight_kernel(const float* __restrict__ w, const float* __restrict__ ch_scale, float* __restrict__ out,
+                                      int C, int K, int KD, int c0, int C_total) {
+  const int n = C * K * K;
+  const int off = (KD - K) / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int kx = i % K, ky = (i / K) % K, c = i / (K * K);
+    out[((ky + off) * KD + kx + off) * C_total + c0 + c] = w[i] * (ch_scale ? ch_scale[c] : 1.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm, any width
+// one warp per token, C <= 512 (16 values per lane)
+__global__ void __launch_bounds__(256) ln_split_generic_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, __half* __restrict__ hi,
+                                                               __half* __restrict__ lo, float scale, int M, int C, float eps,
+                                                               int* status) {
+  constexpr int VMAX = 16;
+  const int token = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (token >= M) return;
+  const float* row = x + static_cast<size_t>(token) * C;
+  float v[VMAX];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < C ? row[c] : 0.f;
+    s += v[i];
+  }
+  const float inv_c = 1.f / static_cast<float>(C);
+  const float mean = warp_sum(s) * inv_c;
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    const float d = (lane + 32 * i < C) ? v[i] - mean : 0.f;
+    s2 = fmaf(d, d, s2);
+  }
+  const float rstd = rsqrtf(warp_sum(s2) * inv_c + eps);
+  bool ov = false;
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) {
+      const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      __half h, l;
+      split_f16(y, scale, h, l, ov);
+      hi[static_cast<size_t>(token) * C + c] = h;
+      lo[static_cast<size_t>(token) * C + c] = l;
+    }
+  }
+  if (ov) atomicOr(status, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ factorised attention
+// qkv: fp32 [B][N][3C] (q | k | v, each head-major h * Ch + c).  Token chunks: chunk j of image b covers tokens
+// [j * tpc, min(N, (j + 1) * tpc)).
+
+// per (image, chunk, channel of k): running max m and sum s = sum exp(k - m) over the chunk's tokens
+__global__ void __launch_bounds__(256) ksoftmax_partial_kernel(const float* __restrict__ qkv, float* __restrict__ part_m,
+                                                               float* __restrict__ part_s, int N, int C, int chunks, int tpc) {
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int n0 = ch * tpc, n1 = min(N, n0 + tpc);
+  const float* base = qkv + static_cast<size_t>(b) * N * 3 * C + C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float m = -INFINITY, s = 0.f;
+    for (int n = n0; n < n1; ++n) {
+      const float k = base[static_cast<size_t>(n) * 3 * C + c];
+      if (k > m) {
+        s = s * expf(m - k) + 1.f;
+        m = k;
+      } else {
+        s += expf(k - m);
+      }
+    }
+    part_m[(static_cast<size_t>(b) * chunks + ch) * C + c] = m;
+    part_s[(static_cast<size_t>(b) * chunks + ch) * C + c] = s;
+  }
+}
+
+// ordered combine over the chunks: colmax[b][c] = max k, colinv[b][c] = 1 / sum exp(k - max)
+__global__ void __launch_bounds__(256) ksoftmax_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
+                                                               float* __restrict__ colmax, float* __restrict__ colinv, int C,
+                                                               int chunks) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float M = -INFINITY;
+    for (int j = 0; j < chunks; ++j) M = fmaxf(M, part_m[(static_cast<size_t>(b) * chunks + j) * C + c]);
+    float S = 0.f;
+    for (int j = 0; j < chunks; ++j) {
+      const size_t o = (static_cast<size_t>(b) * chunks + j) * C + c;
+      S += part_s[o] * expf(part_m[o] - M);
+    }
+    colmax[b * C + c] = M;
+    colinv[b * C + c] = 1.f / S;
+  }
+}
+
+// per (image, head, chunk): part[c1][c2] = sum over the chunk's tokens of exp(k[n][c1] - colmax[c1]) * v[n][c2].
+// 256 threads own <= KTV_NP (c1, c2) pairs each (Ch <= 64); tokens are staged 32 at a time in shared memory.
+constexpr int KTV_NP = 16;
+constexpr int KTV_T = 32;
+constexpr int KTV_CH_MAX = 64;
+__global__ void __launch_bounds__(256) ktv_partial_kernel(const float* __restrict__ qkv, const float* __restrict__ colmax,
+                                                          float* __restrict__ part, int N, int C, int Ch, int heads, int chunks,
+                                                          int tpc) {
+  __shared__ float ek[KTV_T][KTV_CH_MAX];
+  __shared__ float vv[KTV_T][KTV_CH_MAX];
+  const int ch = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n0 = ch * tpc, n1 = min(N, n0 + tpc);
+  const int pairs = Ch * Ch;
+  float acc[KTV_NP];
+  int off[KTV_NP];  // c1 | c2 << 16
+#pragma unroll
+  for (int i = 0; i < KTV_NP; ++i) {
+    acc[i] = 0.f;
+    const int p = threadIdx.x + 256 * i;
+    off[i] = p < pairs ? ((p / Ch) | ((p % Ch) << 16)) : -1;
+  }
+  const float* base = qkv + static_cast<size_t>(b) * N * 3 * C + h * Ch;
+  const float* cmax = colmax + b * C + h * Ch;
+  for (int t0 = n0; t0 < n1; t0 += KTV_T) {
+    for (int i = threadIdx.x; i < KTV_T * Ch; i += 256) {
+      const int tok = i / Ch, c = i - tok * Ch;
+      const int n = t0 + tok;
+      float e = 0.f, v = 0.f;
+      if (n < n1) {
+        const float* row = base + static_cast<size_t>(n) * 3 * C;
+        e = expf(row[C + c] - cmax[c]);
+        v = row[2 * C + c];
+      }
+      ek[tok][c] = e;
+      vv[tok][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < KTV_NP; ++i) {
+      if (off[i] >= 0) {
+        const int c1 = off[i] & 0xffff, c2 = off[i] >> 16;
+        float s = acc[i];
+#pragma unroll 8
+        for (int tok = 0; tok < KTV_T; ++tok) s = fmaf(ek[tok][c1], vv[tok][c2], s);
+        acc[i] = s;
+      }
+    }
+    __syncthreads();
+  }
+  float* dst = part + ((static_cast<size_t>(b) * chunks + ch) * heads + h) * pairs;
+#pragma unroll
+  for (int i = 0; i < KTV_NP; ++i)
+    if (off[i] >= 0) dst[threadIdx.x + 256 * i] = acc[i];
+}
+
+// ordered sum over the chunks, times 1 / sum exp of the k column: ktv[b][h][c1][c2]
+__global__ void __launch_bounds__(256) ktv_combine_kernel(const float* __restrict__ part, const float* __restrict__ colinv,
+                                                          float* __restrict__ ktv, int C, int Ch, int heads, int chunks) {
+  const int b = blockIdx.y;
+  const int total = heads * Ch * Ch;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= total) return;
+  float s = 0.f;
+  for (int j = 0; j < chunks; ++j) s += part[(static_cast<size_t>(b) * chunks + j) * total + p];
+  const int h = p / (Ch * Ch), c1 = (p / Ch) % Ch;
+  ktv[static_cast<size_t>(b) * total + p] = s * colinv[b * C + h * Ch + c1];
+}
+
+// out[n][h Ch + c] = scale * sum_c' q[n][h][c'] ktv[h][c'][c] + q[n][h][c] * (dwconv_win(h)(v)[n][h Ch + c] + bias)
+// One block = FA_T consecutive tokens of one image; shared memory: ktv of the image [heads Ch Ch] + the tile's q [FA_T][C].
+constexpr int FA_T = 32;
+struct FactorApplyArgs {
+  const float* qkv;     // [B][N][3C]
+  const float* ktv;     // [B][heads][Ch][Ch]
+  const float* crpe_w;  // [49][C]: each channel's window centred in a 7 x 7 layout (zeros outside)
+  const float* crpe_b;  // [C]
+  __half* out_hi;       // planes [B][N][C] of split_scale * out
+  __half* out_lo;
+  float split_scale, scale;
+  int B, H, W, C, Ch, heads;
+  int radius[16];       // per head: window / 2
+  int* status;
+};
+__global__ void __launch_bounds__(256) factor_att_apply_kernel(const FactorApplyArgs a) {
+  extern __shared__ float fa_smem[];
+  const int N = a.H * a.W;
+  const int tiles = (N + FA_T - 1) / FA_T;
+  const int b = blockIdx.x / tiles, n0 = (blockIdx.x % tiles) * FA_T;
+  const int nk = a.heads * a.Ch * a.Ch;
+  float* sktv = fa_smem;
+  float* sq = fa_smem + nk;
+  for (int i = threadIdx.x; i < nk; i += 256) sktv[i] = a.ktv[static_cast<size_t>(b) * nk + i];
+  const float* img = a.qkv + static_cast<size_t>(b) * N * 3 * a.C;
+  for (int i = threadIdx.x; i < FA_T * a.C; i += 256) {
+    const int tok = i / a.C, c = i - tok * a.C;
+    sq[i] = (n0 + tok < N) ? img[static_cast<size_t>(n0 + tok) * 3 * a.C + c] : 0.f;
+  }
+  __syncthreads();
+  bool ov = false;
+  for (int i = threadIdx.x; i < FA_T * a.C; i += 256) {
+    const int tok = i / a.C, ch = i - tok * a.C;
+    const int n = n0 + tok;
+    if (n >= N) break;
+    const int h = ch / a.Ch, c = ch - h * a.Ch;
+    const float* qrow = sq + tok * a.C + h * a.Ch;
+    const float* kt = sktv + h * a.Ch * a.Ch + c;
+    float fa = 0.f;
+    for (int k = 0; k < a.Ch; ++k) fa = fmaf(qrow[k], kt[k * a.Ch], fa);
+    const int y = n / a.W, x = n - y * a.W;
+    const int r = a.radius[h];
+    float conv = a.crpe_b[ch];
+    for (int dy = -r; dy <= r; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= a.H) continue;
+      for (int dx = -r; dx <= r; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= a.W) continue;
+        conv = fmaf(__ldg(a.crpe_w + ((dy + 3) * 7 + dx + 3) * a.C + ch),
+                    __ldg(img + (static_cast<size_t>(yy) * a.W + xx) * 3 * a.C + 2 * a.C + ch), conv);
+      }
+    }
+    const float out = a.scale * fa + qrow[c] * conv;
+    __half hh, ll;
+    split_f16(out, a.split_scale, hh, ll, ov);
+    const size_t o = (static_cast<size_t>(b) * N + n) * a.C + ch;
+    a.out_hi[o] = hh;
+    a.out_lo[o] = ll;
+  }
+  if (ov) atomicOr(a.status, 1);
+}
+
+}  // namespace dd

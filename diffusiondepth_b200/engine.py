@@ -136,14 +136,17 @@ class DenoiseEngine:
         self._ws = None
 
     def enable_backbone(self, image_hw, embed_dims=192, depths=(2, 2, 18, 2), num_heads=(6, 12, 24, 48), window=7,
-                        kind="swin"):
-        """Run the backbone natively as well (after enable_producers, before load_weights).  kind: 'swin' (Swin-L) or
-        'resnet' (ResNetForMMBEV BasicBlock stages; only `depths` is used)."""
+                        kind="swin", mp_dims=(64, 128, 216, 288), mp_paths=(2, 3, 3, 3), mlp_ratio=4):
+        """Run the backbone natively as well (after enable_producers, before load_weights).  kind: 'swin' (Swin-L),
+        'resnet' (ResNetForMMBEV BasicBlock stages; only `depths` is used) or 'mpvit' (`depths` = encoder layers per
+        stage, `mp_dims` / `mp_paths` / `mlp_ratio`)."""
         bc = _cabi.DDBackboneConfig()
-        bc.kind, bc.embed_dims, bc.window = (1 if kind == "swin" else 2), int(embed_dims), int(window)
+        bc.kind, bc.embed_dims, bc.window = {"swin": 1, "resnet": 2, "mpvit": 3}[kind], int(embed_dims), int(window)
         bc.height, bc.width = int(image_hw[0]), int(image_hw[1])
+        bc.mlp_ratio = int(mlp_ratio)
         for i in range(4):
             bc.depths[i], bc.num_heads[i] = int(depths[i]), int(num_heads[i])
+            bc.mp_dims[i], bc.mp_paths[i] = int(mp_dims[i]), int(mp_paths[i])
         _cabi.check(self.lib.dd_enable_backbone(self._h, C.byref(bc)))
         self.backbone = (tuple(image_hw), int(embed_dims))
         self._ws = None

@@ -231,16 +231,43 @@ class DDIMHeadBase(nn.Module):
             sizes.append((h, w))
         return sizes
 
-    def backbone_pyramid(self, image_hw):
-        return self.swin_pyramid(image_hw) if self.variant == "swin" else self.resnet_pyramid(image_hw)
+    def backbone_pyramid(self, image_hw, backbone=None):
+        """Stage output sizes of this head's backbone family (MPViT halves per stage like the stem-less ResNet)."""
+        if self.variant == "swin" and type(backbone).__name__ != "MPViT":
+            return self.swin_pyramid(image_hw)
+        return self.resnet_pyramid(image_hw)
+
+    @staticmethod
+    def mpvit_spec(backbone):
+        """(layers per stage, stage widths, paths per stage, mlp ratio) of an MPViT module, or None when it is not one of
+        the shapes the engine instantiates (8 heads, crpe windows {3: 2, 5: 3, 7: 3}, <= 3 paths, widths <= 512)."""
+        try:
+            stages = backbone.mhca_stages
+            dims = [st.InvRes.conv1.conv.in_channels for st in stages]
+            paths = [len(st.mhca_blks) for st in stages]
+            layers = [len(st.mhca_blks[0].MHCA_layers) for st in stages]
+            blk = stages[0].mhca_blks[0].MHCA_layers[0]
+            ratio = blk.mlp.fc1.out_features // dims[0]
+            ok = (len(stages) == 4 and max(paths) <= 3 and max(dims) <= 512 and all(d % 8 == 0 for d in dims)
+                  and dims[0] % 16 == 0 and blk.factoratt_crpe.num_heads == 8
+                  and [c.kernel_size[0] for c in stages[0].mhca_blks[0].crpe.conv_list] == [3, 5, 7]
+                  and all(st.mhca_blks[0].MHCA_layers[0].mlp.fc1.out_features == ratio * d for st, d in zip(stages, dims))
+                  and list(backbone.out_channels) == dims[1:] + dims[-1:])
+            return (layers, dims, paths, ratio) if ok else None
+        except (AttributeError, IndexError):
+            return None
 
     def can_run_backbone(self, backbone, img) -> bool:
         """Native backbone path: CUDA input and an architecture the engine instantiates — Swin-L for the Swin heads,
-        BasicBlock ResNetForMMBEV (64/128/256/512, stride 2 per stage) for the Res heads."""
+        BasicBlock ResNetForMMBEV (64/128/256/512, stride 2 per stage) for the Res heads, MPViT for the MPViT head."""
         if not (self.native_producers and self.native_backbone and img.is_cuda):
             return False
         name = type(backbone).__name__
-        if self.variant == "swin":
+        if name == "MPViT":
+            spec = self.mpvit_spec(backbone)
+            if spec is None or self.variant != "swin" or list(self.fpn_in_channels) != list(backbone.out_channels):
+                return False
+        elif self.variant == "swin":
             if name != "SwinTransformer" or getattr(backbone, "num_features", None) != [192, 384, 768, 1536]:
                 return False
             if [len(s.blocks) for s in backbone.stages] != [2, 2, 18, 2]:
@@ -250,7 +277,7 @@ class DDIMHeadBase(nn.Module):
                 return False
             if [st[0].conv2.out_channels for st in backbone.layers] != [64, 128, 256, 512]:
                 return False
-        return self._sizes_ok(self.backbone_pyramid(img.shape[-2:]))
+        return self._sizes_ok(self.backbone_pyramid(img.shape[-2:], backbone))
 
     def _gather(self, native, image_hw, backbone):
         tensors = self._engine_tensors()
@@ -286,7 +313,10 @@ class DDIMHeadBase(nn.Module):
             if native:
                 eng.enable_producers(feats[0], feats[1], has_neck=self.has_neck)
             if image_hw is not None:
-                if self.variant == "swin":
+                if type(self._backbone(backbone)).__name__ == "MPViT":
+                    layers, dims, paths, ratio = self.mpvit_spec(self._backbone(backbone))
+                    eng.enable_backbone(image_hw, depths=layers, kind="mpvit", mp_dims=dims, mp_paths=paths, mlp_ratio=ratio)
+                elif self.variant == "swin":
                     eng.enable_backbone(image_hw)
                 else:
                     eng.enable_backbone(image_hw, depths=[len(st) for st in self._backbone(backbone).layers], kind="resnet")
@@ -369,7 +399,7 @@ class DDIMHeadBase(nn.Module):
         with_backbone = fp is None
         if with_backbone:
             B, dev, dtype = image.shape[0], image.device, torch.float32
-            sizes = self.backbone_pyramid(image.shape[-2:])
+            sizes = self.backbone_pyramid(image.shape[-2:], self._backbone(backbone))
             native = True
         else:
             if self.detach_fp is not False and self.detach_fp is not None:

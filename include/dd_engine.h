@@ -146,9 +146,16 @@ int dd_build_condition(dd_handle h, const float* const* feats, float* cond_out, 
  * needed).  Instantiated for Swin-L (embed_dims 192, head_dim 32, window 7). */
 enum dd_backbone_kind {
   DD_BACKBONE_SWIN = 1,   /* SwinTransformer (reference backbone/swin.py) */
-  DD_BACKBONE_RESNET = 2  /* ResNetForMMBEV with BasicBlocks, no stem (reference backbone/mmbev_resnet.py:124-187): depths[] =
+  DD_BACKBONE_RESNET = 2, /* ResNetForMMBEV with BasicBlocks, no stem (reference backbone/mmbev_resnet.py:124-187): depths[] =
                              blocks per stage, channels 64/128/256/512, every stage stride 2; needs
                              dd_enable_producers(4 levels, has_neck = 0); embed_dims / num_heads / window ignored */
+  DD_BACKBONE_MPVIT = 3   /* MPViT (reference backbone/mpvit.py:601-730; tiny / xsmall / small / base factories :743-870):
+                             full-resolution stem, then 4 x { chained depthwise-separable patch embeddings (first one
+                             stride 2), a conv path + one factorised-attention encoder per embedding, 1x1 aggregate }.
+                             depths[] = encoder layers per stage, mp_dims[] = stage widths (multiples of 8, <= 512; stage
+                             s outputs mp_dims[s + 1], the last one mp_dims[3]), mp_paths[] = embeddings per stage (<= 3),
+                             mlp_ratio; 8 heads, crpe windows {3: 2, 5: 3, 7: 3} heads.  Outputs at 1/2 .. 1/16 of the image;
+                             needs dd_enable_producers(4 levels) with those sizes and channels */
 };
 typedef struct dd_backbone_config {
   int32_t kind;        /* enum dd_backbone_kind */
@@ -157,6 +164,9 @@ typedef struct dd_backbone_config {
   int32_t num_heads[4];/* 6, 12, 24, 48 */
   int32_t window;      /* 7 */
   int32_t height, width; /* input image size */
+  int32_t mp_dims[4];  /* DD_BACKBONE_MPVIT only: 64, 128, 216, 288 (mpvit_small) */
+  int32_t mp_paths[4]; /* 2, 3, 3, 3 */
+  int32_t mlp_ratio;   /* 4 */
 } dd_backbone_config;
 int dd_enable_backbone(dd_handle h, const dd_backbone_config* bc);
 
