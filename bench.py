@@ -6,8 +6,11 @@
 
 A "step" is one forward of the per-GPU batch (BASELINE config 3: 4 images, 352x1216, Swin-L, T=20) through the
 plugin (`Diffusion_DCbase_Model.forward`): Swin-L backbone + HAHI neck + FPN + T-step DDIM loop + decoder, all
-inside the CUDA engine (no torch compute op is left on the path); for N > 1 the batch shards by rank (weak scaling: 4 images/GPU = BASELINE config 4
-at N = 8) and each step ends with the single all-gather of the depth maps.
+inside the CUDA engine (no torch compute op is left on the path); for N > 1 the batch shards by rank (weak scaling: 4
+images/GPU = BASELINE config 4 at N = 8).  The path has no exchange step: by default every rank keeps (e2e: copies to
+its own host buffer) the depth maps of its shard and there is NO data-path collective; `--gather step` adds an
+all-gather of the depth maps per step on a side stream (`shard.DepthGatherer`; what nn.DataParallel's gather does in
+the reference, src/main.py:434), `--gather blocking` waits for it on the compute stream (the round-1 behaviour).
 """
 import argparse
 import json
@@ -133,7 +136,9 @@ def main():
     ap.add_argument("--workload", default="C3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--blocking-gather", action="store_true", help="N > 1: wait for each step's all-gather on the compute stream (round-1 behaviour)")
+    ap.add_argument("--gather", default="none", choices=["none", "step", "blocking"],
+                    help="N > 1: none = no data-path collective (each rank keeps its shard's depth maps); step = all-gather "
+                         "them every step on a side stream; blocking = ... and wait for it on the compute stream")
     ap.add_argument("--exact", action="store_true", help="exact 3-pass fp16 split everywhere (no fp8 correction products)")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads for the CPU reference (0 = physical cores)")
     args = ap.parse_args()
@@ -144,7 +149,10 @@ def main():
     family, T, B, H, W, gflop_map = WORKLOADS[args.workload]
     METRIC = METRICS[args.workload]
     cfg = {"workload": f"{args.workload}: {family} backbone, T={T} DDIM steps, {B}x{H}x{W} per GPU (synthetic)",
-           "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}",
+           "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}" + ("" if world == 1 else {
+               "none": ", no data-path collective (each rank keeps its shard's depth maps)",
+               "step": ", all-gather of the depth maps every step on a side stream",
+               "blocking": ", blocking all-gather of the depth maps every step"}[args.gather]),
            "l2": "per-step working set ~1.3 GB of activations streamed per conv >> 126 MB L2 (no cross-step reuse)"}
 
     def host_threads():
@@ -202,7 +210,7 @@ def main():
 
     # N > 1: the single collective of the path (all-gather of the depth maps) runs on a side stream into rotating buffers
     # (shard.DepthGatherer), so no rank's next step queues behind a slower peer's current one
-    gatherer = shard.DepthGatherer(B * world) if world > 1 else None
+    gatherer = shard.DepthGatherer(B * world) if world > 1 and args.gather != "none" else None
 
     def step_resident():
         with torch.no_grad():
@@ -210,7 +218,7 @@ def main():
         pred = out["pred"]
         if gatherer is None:
             return pred
-        return gatherer.result(gatherer.submit(pred)) if args.blocking_gather else gatherer.submit(pred)
+        return gatherer.result(gatherer.submit(pred)) if args.gather == "blocking" else gatherer.submit(pred)
 
     # end to end = the call a user of the reference makes (src/main.py:456-470): pinned host sample -> device ->
     # net(sample) -> host, every step; the initial latent is drawn on the device by the head, exactly as the reference
@@ -231,8 +239,9 @@ def main():
         # the same call with nothing overlapped: copy in, compute, blocking copy out
         with torch.no_grad():
             out = model({k: v.to(dev, non_blocking=True) for k, v in host.items() if k != "noise"})
-        pred = shard.gather_depth(out["pred"], B * world) if world > 1 else out["pred"]
-        return pred[first:first + B].to("cpu", non_blocking=False)
+        if gatherer is None:
+            return out["pred"].to("cpu", non_blocking=False)
+        return shard.gather_depth(out["pred"], B * world)[first:first + B].to("cpu", non_blocking=False)
 
     def step_e2e():
         cur = torch.cuda.current_stream()
@@ -243,11 +252,11 @@ def main():
         pending["inputs"] = fetch_inputs()  # next step's host->device copy overlaps this step's compute
         with torch.no_grad():
             out = model(d)
-        pred = gatherer.result(gatherer.submit(out["pred"])) if world > 1 else out["pred"]
+        pred = gatherer.result(gatherer.submit(out["pred"]))[first:first + B] if gatherer is not None else out["pred"]
         if pending["done"] is not None:
             pending["done"].synchronize()  # the previous step's result is now readable on the host
         slot = pending["slot"]
-        out_host[slot].copy_(pred[first:first + B], non_blocking=True)
+        out_host[slot].copy_(pred, non_blocking=True)
         done = torch.cuda.Event()
         done.record(cur)
         pending["done"], pending["slot"] = done, slot ^ 1
@@ -290,7 +299,7 @@ def main():
         sampler.start()
     ms = timed(step_resident, args.steps, "resident")
     clocks = sampler.stop() if sampler else None
-    if world > 1:
+    if gatherer is not None:
         # the same steps WITHOUT the collective: each rank's own pace.  With it, every rank's clock stops when the slowest
         # peer has delivered its last shard, so `resident` shows one number for all ranks; this one shows the spread
         # (power-capped GPUs of one box differ by a few per cent) that bounds weak-scaling efficiency from outside.
@@ -304,6 +313,13 @@ def main():
     ms_e2e = timed(step_e2e, args.steps, "e2e")
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
     ms_serial = timed(step_e2e_serial, args.steps)
+    rank_means = None
+    if world > 1:  # outside the timed regions: every rank really produced its shard (different images -> different means)
+        with torch.no_grad():
+            pm = model(resident)["pred"].clamp(max=1e3).mean().reshape(1)
+        allm = [torch.zeros_like(pm) for _ in range(world)]
+        dist.all_gather(allm, pm)
+        rank_means = [float(t.item()) for t in allm]
     h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "noise")
     d2h = B * H * W * 4
 
@@ -374,7 +390,7 @@ def main():
                       (")" if args.exact or family != "swinl" else "; convA/convB: fp16 hi*hi + two e4m3 correction products)")),
             "data": "synthetic",
             "config": cfg, "clocks": clocks, "gpu_launches": launches, "parity": parity,
-            "per_rank_ms_per_step": per_rank or None,
+            "per_rank_ms_per_step": per_rank or None, "per_rank_output_mean": rank_means,
             "e2e": {"value": e2e_value, "unit": "maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
                     "serial": {"value": B * world * args.steps / (ms_serial / 1e3), "ms_per_step": ms_serial / args.steps,
