@@ -204,9 +204,6 @@ cudaError_t configure_all_kernels() {
                                 dd::WAU_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dd::decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dd::DEC_SMEM)) != cudaSuccess)
     return e;
-  // k^T v of one image (8 heads x Ch^2, Ch <= 64) + a 32-token tile of q (C <= 512)
-  if ((e = cudaFuncSetAttribute(dd::factor_att_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (8 * dd::KTV_CH_MAX * dd::KTV_CH_MAX + dd::FA_T * 512) * 4)) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<16, 64, 16>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<64, 256, 32>()) != cudaSuccess) return e;
   if ((e = configure_umma_all_epi<256, 256, 32>()) != cudaSuccess) return e;
@@ -484,9 +481,9 @@ struct MPViTW {
   float* E[4] = {nullptr, nullptr, nullptr, nullptr};  // the paths' token maps + one swap buffer
   float* R1 = nullptr;
   float* QKV = nullptr;
-  float *part_m = nullptr, *part_s = nullptr, *colmax = nullptr, *colinv = nullptr, *part_ktv = nullptr, *ktv = nullptr;
+  float *part_m = nullptr, *part_s = nullptr, *colinv = nullptr, *part_ktv = nullptr, *ktv = nullptr;
 };
-constexpr int kMpChunksMax = 128;  // token chunks of the factorised attention's reductions
+constexpr int kMpChunksMax = 256;  // token chunks of the factorised attention's reductions
 
 }  // namespace
 
@@ -725,7 +722,6 @@ size_t carve(dd_engine* e, void* base) {
     const size_t chm = static_cast<size_t>(cmax / mc.heads), nk = static_cast<size_t>(mc.heads) * chm * chm;
     mv->part_m = c.take<float>(static_cast<size_t>(g.B) * kMpChunksMax * cmax);
     mv->part_s = c.take<float>(static_cast<size_t>(g.B) * kMpChunksMax * cmax);
-    mv->colmax = c.take<float>(static_cast<size_t>(g.B) * cmax);
     mv->colinv = c.take<float>(static_cast<size_t>(g.B) * cmax);
     mv->part_ktv = c.take<float>(static_cast<size_t>(g.B) * kMpChunksMax * nk);
     mv->ktv = c.take<float>(static_cast<size_t>(g.B) * nk);

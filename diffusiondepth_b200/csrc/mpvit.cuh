@@ -4,8 +4,9 @@
 //   dwconv_nhwc_kernel        depthwise k x k (stride 1 / 2), + bias / folded eval-BN, Hardswish, residual (ConvPosEnc),
 //                             fp32 and / or fp16 hi/lo plane outputs                      (:125-175, :241-259, :482-532)
 //   ln_split_generic_kernel   LayerNorm(C) for any C <= 512 -> planes                     (:396-436)
-//   ksoftmax_*                softmax of k over the TOKEN axis: per-chunk online max / sum, ordered combine  (:374)
-//   ktv_*                     k_softmax^T v per (image, head): per-chunk partial [Ch x Ch] sums, ordered combine (:375)
+//   ksoftmax_partial_kernel   softmax of k over the TOKEN axis: per-chunk online max / sum            (:374)
+//   ktv_{partial,combine}     k_softmax^T v per (image, head): per-chunk partial [Ch x Ch] sums (the chunk maxima are
+//                             folded on the way in), ordered combine                              (:375)
 //   factor_att_apply_kernel   scale * q (k^T v) + q * depthwise_conv_{3,5,7}(v)  -> planes (:376-386, :262-330)
 // All reductions over tokens run in a fixed order (chunk partials, then an ordered combine): results are bit-reproducible.
 #pragma once
@@ -98,12 +99,12 @@ __global__ void pack_dw_weight_kernel(const float* __restrict__ w, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm, any width
-// one warp per token, C <= 512 (16 values per lane)
+// one warp per token, C <= 32 * VMAX (VMAX values per lane: 2 / 4 / 8 / 16 picked by the host from C)
+template <int VMAX>
 __global__ void __launch_bounds__(256) ln_split_generic_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, __half* __restrict__ hi,
                                                                __half* __restrict__ lo, float scale, int M, int C, float eps,
                                                                int* status) {
-  constexpr int VMAX = 16;
   const int token = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (token >= M) return;
@@ -142,61 +143,89 @@ __global__ void __launch_bounds__(256) ln_split_generic_kernel(const float* __re
 
 // ------------------------------------------------------------------------------------------------ factorised attention
 // qkv: fp32 [B][N][3C] (q | k | v, each head-major h * Ch + c).  Token chunks: chunk j of image b covers tokens
-// [j * tpc, min(N, (j + 1) * tpc)).
+// [j * tpc, min(N, (j + 1) * tpc)).  Launch order per layer: ksoftmax_partial -> ktv_partial -> ktv_combine ->
+// factor_att_apply (first round-2 version: 5 kernels, the apply one with 53 blocks of scalar gathers took 275 us on the
+// deepest stage; ncu launch list profiles/r02_launches_mpvit_B1.csv).
 
-// per (image, chunk, channel of k): running max m and sum s = sum exp(k - m) over the chunk's tokens
+// per (image, chunk, channel of k): running max m and sum s = sum exp(k - m) over the chunk's tokens.  256 threads =
+// (256 / C) token slices x C channels; the slices of a channel are merged in slice order.
 __global__ void __launch_bounds__(256) ksoftmax_partial_kernel(const float* __restrict__ qkv, float* __restrict__ part_m,
                                                                float* __restrict__ part_s, int N, int C, int chunks, int tpc) {
+  __shared__ float sm_m[256], sm_s[256];
   const int b = blockIdx.y, ch = blockIdx.x;
   const int n0 = ch * tpc, n1 = min(N, n0 + tpc);
   const float* base = qkv + static_cast<size_t>(b) * N * 3 * C + C;
-  for (int c = threadIdx.x; c < C; c += 256) {
+  const int nsl = C >= 256 ? 1 : 256 / C;
+  const int slice = nsl == 1 ? 0 : threadIdx.x / C;
+  const int c_first = nsl == 1 ? threadIdx.x : threadIdx.x - slice * C;
+  for (int c = c_first; c < C; c += 256) {  // more than one trip only when C > 256 (then nsl == 1)
     float m = -INFINITY, s = 0.f;
-    for (int n = n0; n < n1; ++n) {
-      const float k = base[static_cast<size_t>(n) * 3 * C + c];
-      if (k > m) {
-        s = s * expf(m - k) + 1.f;
-        m = k;
-      } else {
-        s += expf(k - m);
+    if (slice < nsl) {
+      for (int n = n0 + slice; n < n1; n += nsl) {
+        const float k = base[static_cast<size_t>(n) * 3 * C + c];
+        if (k > m) {
+          s = s * expf(m - k) + 1.f;
+          m = k;
+        } else {
+          s += expf(k - m);
+        }
       }
     }
-    part_m[(static_cast<size_t>(b) * chunks + ch) * C + c] = m;
-    part_s[(static_cast<size_t>(b) * chunks + ch) * C + c] = s;
-  }
-}
-
-// ordered combine over the chunks: colmax[b][c] = max k, colinv[b][c] = 1 / sum exp(k - max)
-__global__ void __launch_bounds__(256) ksoftmax_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_s,
-                                                               float* __restrict__ colmax, float* __restrict__ colinv, int C,
-                                                               int chunks) {
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float M = -INFINITY;
-    for (int j = 0; j < chunks; ++j) M = fmaxf(M, part_m[(static_cast<size_t>(b) * chunks + j) * C + c]);
-    float S = 0.f;
-    for (int j = 0; j < chunks; ++j) {
-      const size_t o = (static_cast<size_t>(b) * chunks + j) * C + c;
-      S += part_s[o] * expf(part_m[o] - M);
+    if (nsl > 1) {
+      __syncthreads();
+      if (slice < nsl) {
+        sm_m[threadIdx.x] = m;
+        sm_s[threadIdx.x] = s;
+      }
+      __syncthreads();
+      if (slice == 0) {
+        for (int j = 1; j < nsl; ++j) {
+          const float mj = sm_m[j * C + c], sj = sm_s[j * C + c];
+          if (sj > 0.f) {
+            const float mm = fmaxf(m, mj);
+            s = s * expf(m - mm) + sj * expf(mj - mm);
+            m = mm;
+          }
+        }
+      }
     }
-    colmax[b * C + c] = M;
-    colinv[b * C + c] = 1.f / S;
+    if (slice == 0) {
+      part_m[(static_cast<size_t>(b) * chunks + ch) * C + c] = m;
+      part_s[(static_cast<size_t>(b) * chunks + ch) * C + c] = s;
+    }
   }
 }
 
 // per (image, head, chunk): part[c1][c2] = sum over the chunk's tokens of exp(k[n][c1] - colmax[c1]) * v[n][c2].
-// 256 threads own <= KTV_NP (c1, c2) pairs each (Ch <= 64); tokens are staged 32 at a time in shared memory.
+// The block first folds the chunk partials of its head's k columns into colmax / 1 / sum exp (chunk 0's blocks also store
+// them for ktv_combine).  256 threads own <= KTV_NP (c1, c2) pairs each (Ch <= 64); tokens are staged 32 at a time.
 constexpr int KTV_NP = 16;
 constexpr int KTV_T = 32;
 constexpr int KTV_CH_MAX = 64;
-__global__ void __launch_bounds__(256) ktv_partial_kernel(const float* __restrict__ qkv, const float* __restrict__ colmax,
+__global__ void __launch_bounds__(256) ktv_partial_kernel(const float* __restrict__ qkv, const float* __restrict__ part_m,
+                                                          const float* __restrict__ part_s, float* __restrict__ colinv,
                                                           float* __restrict__ part, int N, int C, int Ch, int heads, int chunks,
                                                           int tpc) {
   __shared__ float ek[KTV_T][KTV_CH_MAX];
   __shared__ float vv[KTV_T][KTV_CH_MAX];
+  __shared__ float cmax[KTV_CH_MAX];
   const int ch = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int n0 = ch * tpc, n1 = min(N, n0 + tpc);
   const int pairs = Ch * Ch;
+  if (threadIdx.x < Ch) {
+    const int c = h * Ch + threadIdx.x;
+    float M = -INFINITY;
+    for (int j = 0; j < chunks; ++j) M = fmaxf(M, part_m[(static_cast<size_t>(b) * chunks + j) * C + c]);
+    cmax[threadIdx.x] = M;
+    if (ch == 0) {
+      float S = 0.f;
+      for (int j = 0; j < chunks; ++j) {
+        const size_t o = (static_cast<size_t>(b) * chunks + j) * C + c;
+        S += part_s[o] * expf(part_m[o] - M);
+      }
+      colinv[b * C + c] = 1.f / S;
+    }
+  }
   float acc[KTV_NP];
   int off[KTV_NP];  // c1 | c2 << 16
 #pragma unroll
@@ -205,8 +234,8 @@ __global__ void __launch_bounds__(256) ktv_partial_kernel(const float* __restric
     const int p = threadIdx.x + 256 * i;
     off[i] = p < pairs ? ((p / Ch) | ((p % Ch) << 16)) : -1;
   }
+  __syncthreads();
   const float* base = qkv + static_cast<size_t>(b) * N * 3 * C + h * Ch;
-  const float* cmax = colmax + b * C + h * Ch;
   for (int t0 = n0; t0 < n1; t0 += KTV_T) {
     for (int i = threadIdx.x; i < KTV_T * Ch; i += 256) {
       const int tok = i / Ch, c = i - tok * Ch;
@@ -239,26 +268,36 @@ __global__ void __launch_bounds__(256) ktv_partial_kernel(const float* __restric
     if (off[i] >= 0) dst[threadIdx.x + 256 * i] = acc[i];
 }
 
-// ordered sum over the chunks, times 1 / sum exp of the k column: ktv[b][h][c1][c2]
+// sum over the chunks (8 chunk slices per entry, merged in slice order), times 1 / sum exp of the k column:
+// ktv[b][h][c1][c2].  Block = 32 entries x 8 slices.
 __global__ void __launch_bounds__(256) ktv_combine_kernel(const float* __restrict__ part, const float* __restrict__ colinv,
                                                           float* __restrict__ ktv, int C, int Ch, int heads, int chunks) {
+  __shared__ float red[8][32];
   const int b = blockIdx.y;
   const int total = heads * Ch * Ch;
-  const int p = blockIdx.x * 256 + threadIdx.x;
-  if (p >= total) return;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int j = 0; j < chunks; ++j) s += part[(static_cast<size_t>(b) * chunks + j) * total + p];
-  const int h = p / (Ch * Ch), c1 = (p / Ch) % Ch;
-  ktv[static_cast<size_t>(b) * total + p] = s * colinv[b * C + h * Ch + c1];
+  if (p < total)
+    for (int j = slice; j < chunks; j += 8) s += part[(static_cast<size_t>(b) * chunks + j) * total + p];
+  red[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && p < total) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) s += red[j][lane];
+    const int h = p / (Ch * Ch), c1 = (p / Ch) % Ch;
+    ktv[static_cast<size_t>(b) * total + p] = s * colinv[b * C + h * Ch + c1];
+  }
 }
 
 // out[n][h Ch + c] = scale * sum_c' q[n][h][c'] ktv[h][c'][c] + q[n][h][c] * (dwconv_win(h)(v)[n][h Ch + c] + bias)
-// One block = FA_T consecutive tokens of one image; shared memory: ktv of the image [heads Ch Ch] + the tile's q [FA_T][C].
-constexpr int FA_T = 32;
+// One thread = one token x 4 channels: the convolution walks the (2r + 1)^2 window of the widest head among its channels
+// with float4 loads (the table holds every channel's window centred in a 7 x 7 layout, zeros outside), k^T v and the
+// token's q row come through L1 (one image's k^T v is <= 115 KB, the row <= 2 KB).
 struct FactorApplyArgs {
   const float* qkv;     // [B][N][3C]
   const float* ktv;     // [B][heads][Ch][Ch]
-  const float* crpe_w;  // [49][C]: each channel's window centred in a 7 x 7 layout (zeros outside)
+  const float* crpe_w;  // [49][C]
   const float* crpe_b;  // [C]
   __half* out_hi;       // planes [B][N][C] of split_scale * out
   __half* out_lo;
@@ -268,49 +307,69 @@ struct FactorApplyArgs {
   int* status;
 };
 __global__ void __launch_bounds__(256) factor_att_apply_kernel(const FactorApplyArgs a) {
-  extern __shared__ float fa_smem[];
-  const int N = a.H * a.W;
-  const int tiles = (N + FA_T - 1) / FA_T;
-  const int b = blockIdx.x / tiles, n0 = (blockIdx.x % tiles) * FA_T;
-  const int nk = a.heads * a.Ch * a.Ch;
-  float* sktv = fa_smem;
-  float* sq = fa_smem + nk;
-  for (int i = threadIdx.x; i < nk; i += 256) sktv[i] = a.ktv[static_cast<size_t>(b) * nk + i];
-  const float* img = a.qkv + static_cast<size_t>(b) * N * 3 * a.C;
-  for (int i = threadIdx.x; i < FA_T * a.C; i += 256) {
-    const int tok = i / a.C, c = i - tok * a.C;
-    sq[i] = (n0 + tok < N) ? img[static_cast<size_t>(n0 + tok) * 3 * a.C + c] : 0.f;
-  }
-  __syncthreads();
+  const int N = a.H * a.W, C4 = a.C >> 2;
+  const size_t total = static_cast<size_t>(a.B) * N * C4;
   bool ov = false;
-  for (int i = threadIdx.x; i < FA_T * a.C; i += 256) {
-    const int tok = i / a.C, ch = i - tok * a.C;
-    const int n = n0 + tok;
-    if (n >= N) break;
-    const int h = ch / a.Ch, c = ch - h * a.Ch;
-    const float* qrow = sq + tok * a.C + h * a.Ch;
-    const float* kt = sktv + h * a.Ch * a.Ch + c;
-    float fa = 0.f;
-    for (int k = 0; k < a.Ch; ++k) fa = fmaf(qrow[k], kt[k * a.Ch], fa);
+  for (size_t i = blockIdx.x * static_cast<size_t>(256) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * 256) {
+    const int c4 = static_cast<int>(i % C4);
+    const size_t tok = i / C4;
+    const int n = static_cast<int>(tok % N), b = static_cast<int>(tok / N);
     const int y = n / a.W, x = n - y * a.W;
-    const int r = a.radius[h];
-    float conv = a.crpe_b[ch];
+    const int ch = 4 * c4;
+    const int h0 = ch / a.Ch, h3 = (ch + 3) / a.Ch;
+    const int r = max(a.radius[h0], a.radius[h3]);
+    const float* img = a.qkv + static_cast<size_t>(b) * N * 3 * a.C;
+    float4 conv = __ldg(reinterpret_cast<const float4*>(a.crpe_b) + c4);
     for (int dy = -r; dy <= r; ++dy) {
       const int yy = y + dy;
       if (yy < 0 || yy >= a.H) continue;
       for (int dx = -r; dx <= r; ++dx) {
         const int xx = x + dx;
         if (xx < 0 || xx >= a.W) continue;
-        conv = fmaf(__ldg(a.crpe_w + ((dy + 3) * 7 + dx + 3) * a.C + ch),
-                    __ldg(img + (static_cast<size_t>(yy) * a.W + xx) * 3 * a.C + 2 * a.C + ch), conv);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(a.crpe_w + ((dy + 3) * 7 + dx + 3) * a.C) + c4);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(img + (static_cast<size_t>(yy) * a.W + xx) * 3 * a.C + 2 * a.C) + c4);
+        conv.x = fmaf(w.x, v.x, conv.x);
+        conv.y = fmaf(w.y, v.y, conv.y);
+        conv.z = fmaf(w.z, v.z, conv.z);
+        conv.w = fmaf(w.w, v.w, conv.w);
       }
     }
-    const float out = a.scale * fa + qrow[c] * conv;
-    __half hh, ll;
-    split_f16(out, a.split_scale, hh, ll, ov);
-    const size_t o = (static_cast<size_t>(b) * N + n) * a.C + ch;
-    a.out_hi[o] = hh;
-    a.out_lo[o] = ll;
+    const float* qrow = img + static_cast<size_t>(n) * 3 * a.C;
+    const float* kt = a.ktv + static_cast<size_t>(b) * a.heads * a.Ch * a.Ch;
+    float fa[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h0 == h3 && (a.Ch & 3) == 0) {  // the four channels sit in one head at a 16-byte aligned column
+      const float* qh = qrow + h0 * a.Ch;
+      const float* kh = kt + static_cast<size_t>(h0) * a.Ch * a.Ch + (ch - h0 * a.Ch);
+      for (int k = 0; k < a.Ch; ++k) {
+        const float q = __ldg(qh + k);
+        const float4 t = __ldg(reinterpret_cast<const float4*>(kh + k * a.Ch));
+        fa[0] = fmaf(q, t.x, fa[0]);
+        fa[1] = fmaf(q, t.y, fa[1]);
+        fa[2] = fmaf(q, t.z, fa[2]);
+        fa[3] = fmaf(q, t.w, fa[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int hj = (ch + j) / a.Ch, cj = ch + j - hj * a.Ch;
+        const float* qh = qrow + hj * a.Ch;
+        const float* kh = kt + static_cast<size_t>(hj) * a.Ch * a.Ch + cj;
+        float s = 0.f;
+        for (int k = 0; k < a.Ch; ++k) s = fmaf(__ldg(qh + k), __ldg(kh + k * a.Ch), s);
+        fa[j] = s;
+      }
+    }
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(qrow) + c4);
+    const float o0 = fmaf(a.scale, fa[0], q4.x * conv.x), o1 = fmaf(a.scale, fa[1], q4.y * conv.y);
+    const float o2 = fmaf(a.scale, fa[2], q4.z * conv.z), o3 = fmaf(a.scale, fa[3], q4.w * conv.w);
+    __half h[4], l[4];
+    split_f16(o0, a.split_scale, h[0], l[0], ov);
+    split_f16(o1, a.split_scale, h[1], l[1], ov);
+    split_f16(o2, a.split_scale, h[2], l[2], ov);
+    split_f16(o3, a.split_scale, h[3], l[3], ov);
+    const size_t o = tok * a.C + ch;
+    *reinterpret_cast<uint2*>(a.out_hi + o) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(a.out_lo + o) = *reinterpret_cast<const uint2*>(l);
   }
   if (ov) atomicOr(a.status, 1);
 }

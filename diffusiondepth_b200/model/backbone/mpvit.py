@@ -2,8 +2,9 @@
 src/model/backbone/mpvit.py:57-741; the variant the `DDIMDepthEstimate_MPVIT_ADDHAHI` head is trained with is
 `mpvit_small`, README.md:272).  Host-side mirror: a torch module whose `state_dict` loads the released checkpoints
 key for key (including the duplicated keys of the position-encoding modules each encoder shares with its blocks).
-It runs as torch ops under `exact_fp32()` — the engine instantiates Swin-L and BasicBlock ResNets natively, MPViT
-feeds the native loop through the fallback producer path.
+On a CUDA input the plugin does not call this module's forward: the engine runs the network itself from these
+parameters (`dd_run_backbone`, kind DD_BACKBONE_MPVIT — csrc/mpvit.cuh + the GEMM path); the torch forward
+below (under `exact_fp32()`) is what `native_backbone = False` and shapes the engine does not instantiate fall back to.
 
 Structure per stage i (dims C_i -> C_{i+1}):
   patch_embed_stages[i]: a CHAIN of depthwise-separable 3x3 embeddings (dw 3x3, pw 1x1, BN, Hardswish); the first

@@ -45,6 +45,7 @@ GOLDEN = {
 GOLDEN_TRAINED = {
     "g_swinl_small_trained": ("swinl", 5, 1, 96, 160),
     "g_res18_trained": ("res18", 5, 2, 70, 106),
+    "g_mpvit_trained": ("mpvit_s", 5, 2, 70, 106),  # odd sizes on every MPViT level (35x53 .. 5x7), folded BN everywhere
 }
 SEED_TRAINED = 99
 

@@ -19,19 +19,20 @@ sample = restate.synthetic_sample(B, H, W, configs.SEED_INPUTS)
 sample["noise"] = restate.synthetic_noise(B, H, W, configs.SEED_NOISE)
 sample = {k: v.to(dev) for k, v in sample.items()}
 out = {}
-for native in (True, False):
+REPS = int(os.environ.get("DD_REPS", 5))
+for native in ((True,) if os.environ.get("DD_NATIVE_ONLY") else (True, False)):
     m.depth_head.native_backbone = native
     with torch.no_grad():
-        for _ in range(3):
+        for _ in range(min(3, REPS)):
             m(sample)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5):
+        for _ in range(REPS):
             o = m(sample)
         e1.record()
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
+    ms = e0.elapsed_time(e1) / REPS
     eng = next(reversed(m.depth_head._engines.values()))
     out["engine_backbone" if native else "torch_backbone"] = {
         "ms_per_forward": ms, "maps_per_s": B / ms * 1e3, "engine_launches": eng.last_launch_count,
@@ -41,9 +42,9 @@ for native in (True, False):
         eng.run_backbone(sample["rgb"].contiguous().float())
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(5):
+        for _ in range(REPS):
             eng.run_backbone(sample["rgb"].contiguous().float())
         e1.record()
         torch.cuda.synchronize()
-        out["engine_backbone"]["backbone_ms"] = e0.elapsed_time(e1) / 5
+        out["engine_backbone"]["backbone_ms"] = e0.elapsed_time(e1) / REPS
 print(json.dumps({"workload": f"MPViT-small, T={T}, {B}x{H}x{W}", **out}))

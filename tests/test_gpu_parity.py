@@ -366,7 +366,7 @@ def _run_plugin(case, batch=None, fp8=True):
 
 
 @pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_swinl_small", "g_res50_c2", "g_swinl_c3",
-                                  "g_swinl_c5", "g_swinl_add_small", "g_mpvit_small", "g_res18_trained",
+                                  "g_swinl_c5", "g_swinl_add_small", "g_mpvit_small", "g_mpvit_trained", "g_res18_trained",
                                   "g_swinl_small_trained"])
 def test_plugin_forward_matches_reference_golden(case, parity_log):
     """`Diffusion_DCbase_Model.forward(sample)` on the GPU vs the real reference's own forward (golden).  `*_trained`:

@@ -10,7 +10,7 @@ import dd_helpers as helpers
 TOL_Z = 5e-5  # fp32-vs-fp32 re-association noise on the logits (3e-5 vs fp64 over 20 steps)
 
 
-@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small", "g_res18_trained",
+@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small", "g_mpvit_trained", "g_res18_trained",
                                   "g_swinl_small_trained"])
 def test_oracle_reproduces_reference_golden(case):
     """`*_trained`: the trained-like regime (oracle.configs.trainedify: random non-zero Swin relative-position tables,
@@ -38,7 +38,7 @@ def test_oracle_reproduces_reference_golden(case):
         'pred_init', 'pred_inter', 'pred_uncertainty', 'weight_map'])
 
 
-@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small", "g_res18_trained",
+@pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small", "g_mpvit_trained", "g_res18_trained",
                                   "g_swinl_small_trained"])
 def test_mirror_producers_match_reference_condition(case):
     """backbone + FPN of the product mirror (torch ops, once per image) reproduce the reference's cond map."""

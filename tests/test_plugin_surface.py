@@ -82,3 +82,21 @@ def test_state_dict_matches_reference_key_for_key(family):
         mine_fresh = helpers.build_mirror(family, 5)
         assert torch.equal(a[k], mine_fresh.state_dict()[k])
         assert len(a) == 532
+
+
+def test_mpvit_spec_of_every_factory():
+    """What the head hands to dd_enable_backbone(kind = MPViT) is read off the torch module: layers, widths, paths, mlp
+    ratio of the four reference factories (backbone/mpvit.py:743-870); anything the engine does not instantiate -> None."""
+    from diffusiondepth_b200.model.backbone import mpvit
+    from diffusiondepth_b200.model.head._ddim_head import DDIMHeadBase
+    want = {"mpvit_tiny": ([1, 2, 4, 1], [64, 96, 176, 216], [2, 3, 3, 3], 2),
+            "mpvit_xsmall": ([1, 2, 4, 1], [64, 128, 192, 256], [2, 3, 3, 3], 4),
+            "mpvit_small": ([1, 3, 6, 3], [64, 128, 216, 288], [2, 3, 3, 3], 4),
+            "mpvit_base": ([1, 3, 8, 3], [128, 224, 368, 480], [2, 3, 3, 3], 4)}
+    for name, spec in want.items():
+        bb = getattr(mpvit, name)()
+        assert tuple(DDIMHeadBase.mpvit_spec(bb)) == spec, name
+    wide = mpvit.MPViT(num_stages=4, num_path=(2, 3, 3, 3), num_layers=(1, 1, 1, 1), embed_dims=(64, 128, 256, 640),
+                       mlp_ratios=(4,) * 4, num_heads=(8,) * 4)
+    assert DDIMHeadBase.mpvit_spec(wide) is None            # 640 / 8 = 80 channels per head > 64
+    assert DDIMHeadBase.mpvit_spec(torch.nn.Identity()) is None
