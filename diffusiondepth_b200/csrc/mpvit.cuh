@@ -161,14 +161,19 @@ __global__ void __launch_bounds__(256) ksoftmax_partial_kernel(const float* __re
   for (int c = c_first; c < C; c += 256) {  // more than one trip only when C > 256 (then nsl == 1)
     float m = -INFINITY, s = 0.f;
     if (slice < nsl) {
-      for (int n = n0 + slice; n < n1; n += nsl) {
+      int n = n0 + slice;
+      for (; n + 3 * nsl < n1; n += 4 * nsl) {  // four independent loads in flight, one rescale per group
+        const float k0 = base[static_cast<size_t>(n) * 3 * C + c], k1 = base[static_cast<size_t>(n + nsl) * 3 * C + c];
+        const float k2 = base[static_cast<size_t>(n + 2 * nsl) * 3 * C + c], k3 = base[static_cast<size_t>(n + 3 * nsl) * 3 * C + c];
+        const float mm = fmaxf(fmaxf(fmaxf(k0, k1), fmaxf(k2, k3)), m);
+        s = s * expf(m - mm) + ((expf(k0 - mm) + expf(k1 - mm)) + (expf(k2 - mm) + expf(k3 - mm)));
+        m = mm;
+      }
+      for (; n < n1; n += nsl) {
         const float k = base[static_cast<size_t>(n) * 3 * C + c];
-        if (k > m) {
-          s = s * expf(m - k) + 1.f;
-          m = k;
-        } else {
-          s += expf(k - m);
-        }
+        const float mm = fmaxf(m, k);
+        s = s * expf(m - mm) + expf(k - mm);
+        m = mm;
       }
     }
     if (nsl > 1) {
@@ -196,24 +201,29 @@ __global__ void __launch_bounds__(256) ksoftmax_partial_kernel(const float* __re
   }
 }
 
-// per (image, head, chunk): part[c1][c2] = sum over the chunk's tokens of exp(k[n][c1] - colmax[c1]) * v[n][c2].
-// The block first folds the chunk partials of its head's k columns into colmax / 1 / sum exp (chunk 0's blocks also store
-// them for ktv_combine).  256 threads own <= KTV_NP (c1, c2) pairs each (Ch <= 64); tokens are staged 32 at a time.
+// per (image, group of HB heads, chunk): part[h][c1][c2] = sum over the chunk's tokens of exp(k[n][h][c1] - colmax) * v[n][h][c2].
+// The block first folds the chunk partials of its k columns into colmax (chunk 0's blocks also store 1 / sum exp for
+// ktv_combine).  256 threads own <= KTV_NP (h, c1, c2) entries each; the host picks HB with HB Ch^2 <= 4096 and
+// HB Ch <= KTV_W, so that the high-resolution stages (Ch = 8, 16) take all 8 heads in one block (one block per head left
+// 64 threads with 32 FMAs between two barriers: 397 us on stage 0).  Tokens are staged 32 at a time.
 constexpr int KTV_NP = 16;
 constexpr int KTV_T = 32;
+constexpr int KTV_W = 160;
 constexpr int KTV_CH_MAX = 64;
 __global__ void __launch_bounds__(256) ktv_partial_kernel(const float* __restrict__ qkv, const float* __restrict__ part_m,
                                                           const float* __restrict__ part_s, float* __restrict__ colinv,
-                                                          float* __restrict__ part, int N, int C, int Ch, int heads, int chunks,
-                                                          int tpc) {
-  __shared__ float ek[KTV_T][KTV_CH_MAX];
-  __shared__ float vv[KTV_T][KTV_CH_MAX];
-  __shared__ float cmax[KTV_CH_MAX];
-  const int ch = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+                                                          float* __restrict__ part, int N, int C, int Ch, int heads, int HB,
+                                                          int chunks, int tpc) {
+  __shared__ float ek[KTV_T][KTV_W];
+  __shared__ float vv[KTV_T][KTV_W];
+  __shared__ float cmax[KTV_W];
+  const int ch = blockIdx.x, b = blockIdx.z;
+  const int hb0 = blockIdx.y * HB, nh = min(HB, heads - hb0);
+  const int width = nh * Ch, c_base = hb0 * Ch;
   const int n0 = ch * tpc, n1 = min(N, n0 + tpc);
-  const int pairs = Ch * Ch;
-  if (threadIdx.x < Ch) {
-    const int c = h * Ch + threadIdx.x;
+  const int per_head = Ch * Ch, pairs = nh * per_head;
+  if (threadIdx.x < width) {
+    const int c = c_base + threadIdx.x;
     float M = -INFINITY;
     for (int j = 0; j < chunks; ++j) M = fmaxf(M, part_m[(static_cast<size_t>(b) * chunks + j) * C + c]);
     cmax[threadIdx.x] = M;
@@ -227,18 +237,23 @@ __global__ void __launch_bounds__(256) ktv_partial_kernel(const float* __restric
     }
   }
   float acc[KTV_NP];
-  int off[KTV_NP];  // c1 | c2 << 16
+  int off[KTV_NP];  // column of exp(k) | column of v << 16 (both inside the block's [width] slice)
 #pragma unroll
   for (int i = 0; i < KTV_NP; ++i) {
     acc[i] = 0.f;
     const int p = threadIdx.x + 256 * i;
-    off[i] = p < pairs ? ((p / Ch) | ((p % Ch) << 16)) : -1;
+    if (p < pairs) {
+      const int hl = p / per_head, r = p - hl * per_head;
+      off[i] = (hl * Ch + r / Ch) | ((hl * Ch + r % Ch) << 16);
+    } else {
+      off[i] = -1;
+    }
   }
   __syncthreads();
-  const float* base = qkv + static_cast<size_t>(b) * N * 3 * C + h * Ch;
+  const float* base = qkv + static_cast<size_t>(b) * N * 3 * C + c_base;
   for (int t0 = n0; t0 < n1; t0 += KTV_T) {
-    for (int i = threadIdx.x; i < KTV_T * Ch; i += 256) {
-      const int tok = i / Ch, c = i - tok * Ch;
+    for (int i = threadIdx.x; i < KTV_T * width; i += 256) {
+      const int tok = i / width, c = i - tok * width;
       const int n = t0 + tok;
       float e = 0.f, v = 0.f;
       if (n < n1) {
@@ -262,7 +277,7 @@ __global__ void __launch_bounds__(256) ktv_partial_kernel(const float* __restric
     }
     __syncthreads();
   }
-  float* dst = part + ((static_cast<size_t>(b) * chunks + ch) * heads + h) * pairs;
+  float* dst = part + (static_cast<size_t>(b) * chunks + ch) * heads * per_head + static_cast<size_t>(hb0) * per_head;
 #pragma unroll
   for (int i = 0; i < KTV_NP; ++i)
     if (off[i] >= 0) dst[threadIdx.x + 256 * i] = acc[i];
@@ -291,9 +306,11 @@ __global__ void __launch_bounds__(256) ktv_combine_kernel(const float* __restric
 }
 
 // out[n][h Ch + c] = scale * sum_c' q[n][h][c'] ktv[h][c'][c] + q[n][h][c] * (dwconv_win(h)(v)[n][h Ch + c] + bias)
-// One thread = one token x 4 channels: the convolution walks the (2r + 1)^2 window of the widest head among its channels
+// One work item = one token x 4 channels: the convolution walks the (2r + 1)^2 window of the widest head among its channels
 // with float4 loads (the table holds every channel's window centred in a 7 x 7 layout, zeros outside), k^T v and the
-// token's q row come through L1 (one image's k^T v is <= 115 KB, the row <= 2 KB).
+// token's q row come through L1.  One block = a 16 x 8 pixel tile x 64 channels, so that the window overlap of neighbouring
+// pixels in BOTH directions is served by L1 (22 x 14 x 256 B = 79 KB per block: 2.4x the tile instead of the 10x that
+// 16-token row segments pulled from L2 — 252 us per launch on stages 0-2 at B = 4).
 struct FactorApplyArgs {
   const float* qkv;     // [B][N][3C]
   const float* ktv;     // [B][heads][Ch][Ch]
@@ -306,15 +323,24 @@ struct FactorApplyArgs {
   int radius[16];       // per head: window / 2
   int* status;
 };
+constexpr int FA_TX = 16, FA_TY = 8, FA_CC = 16;  // pixel tile, float4 channel groups per block
 __global__ void __launch_bounds__(256) factor_att_apply_kernel(const FactorApplyArgs a) {
   const int N = a.H * a.W, C4 = a.C >> 2;
-  const size_t total = static_cast<size_t>(a.B) * N * C4;
+  const int tiles_x = (a.W + FA_TX - 1) / FA_TX, tiles_y = (a.H + FA_TY - 1) / FA_TY, cchunks = (C4 + FA_CC - 1) / FA_CC;
+  int blk = blockIdx.x;
+  const int cchunk = blk % cchunks; blk /= cchunks;
+  const int tx = blk % tiles_x; blk /= tiles_x;
+  const int ty = blk % tiles_y;
+  const int b = blk / tiles_y;
+  const int cc = min(FA_CC, C4 - cchunk * FA_CC);
   bool ov = false;
-  for (size_t i = blockIdx.x * static_cast<size_t>(256) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * 256) {
-    const int c4 = static_cast<int>(i % C4);
-    const size_t tok = i / C4;
-    const int n = static_cast<int>(tok % N), b = static_cast<int>(tok / N);
-    const int y = n / a.W, x = n - y * a.W;
+  for (int it = threadIdx.x; it < FA_TX * FA_TY * cc; it += 256) {
+    const int c4 = cchunk * FA_CC + it % cc;
+    const int px = it / cc;
+    const int x = tx * FA_TX + px % FA_TX, y = ty * FA_TY + px / FA_TX;
+    if (x >= a.W || y >= a.H) continue;
+    const int n = y * a.W + x;
+    const size_t tok = static_cast<size_t>(b) * N + n;
     const int ch = 4 * c4;
     const int h0 = ch / a.Ch, h3 = (ch + 3) / a.Ch;
     const int r = max(a.radius[h0], a.radius[h3]);
