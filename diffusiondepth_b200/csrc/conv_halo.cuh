@@ -61,7 +61,10 @@ struct HaloCfg {
   static constexpr int B8_TILE = B_ROWS * BK;
   static constexpr int B8_TILE_PAD = (B8_TILE + 1023) / 1024 * 1024;
   static constexpr int B_SLOT = F8 ? B_TILE_PAD + 2 * B8_TILE_PAD : 2 * B_TILE_PAD;
-  static constexpr int A_SLOTS = F8 ? 3 : 2;
+  // F8 with ONE chunk per tile (64 -> 256, K = 576: the epilogue is on the critical path, so it keeps the transposed
+  // coalesced fp32 store and its staging tiles): two strip units instead of three make room for them
+  static constexpr bool F8_NARROW_K = F8 && CIN == 64;
+  static constexpr int A_SLOTS = F8 ? (F8_NARROW_K ? 2 : 3) : 2;
   // Two sets of four epilogue warps where the epilogue is on the critical path: Cout = 64 (two chunks, one per set; each
   // set then owns two GroupNorm groups) and the pair kernel's 64->256 layer (K = 576: 18 stages per tile, so draining a
   // 128 x 256 fp32 tile with one warp per scheduler took as long as the mainloop; the sets take alternate chunks and
@@ -70,7 +73,7 @@ struct HaloCfg {
   static constexpr bool STATS_LOCAL = (COUT == 64);  // a set's chunk(s) cover whole groups of their own
   static constexpr int EPI_WARPS = 4 * EPI_SETS;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
-  static constexpr int XPOSE_BYTES = F8 ? 0 : EPI_WARPS * 32 * 32 * 4;  // F8: fp32 outputs (tests) store row-wise
+  static constexpr int XPOSE_BYTES = (F8 && !F8_NARROW_K) ? 0 : EPI_WARPS * 32 * 32 * 4;  // F8 256 -> 256: fp32 outputs (tests) store row-wise
   static constexpr int BUDGET = 227 * 1024 - 1024 - 1024 - XPOSE_BYTES - A_SLOTS * A_SLOT;
   static constexpr int B_SLOTS_RAW = BUDGET / B_SLOT;
   // Small layers (16->64, 64->16): all 9 x KC weight tiles fit in shared memory -> fetch them ONCE per CTA instead of once
@@ -513,7 +516,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             }
           }
         }
-        if constexpr ((EPI == EPI_F32_STATS || EPI == EPI_F32) && C::CH == 32 && !F8) {
+        if constexpr ((EPI == EPI_F32_STATS || EPI == EPI_F32) && C::CH == 32 && C::XPOSE_BYTES > 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) T[lane * 32 + ((j ^ lane) & 31)] = v[j];
           __syncwarp();

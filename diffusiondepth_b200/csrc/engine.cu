@@ -198,8 +198,6 @@ cudaError_t configure_umma_all_epi() {
 }
 cudaError_t configure_all_kernels() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(dd::gn_apply_up_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                dd::UPK_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dd::window_attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 dd::WAU_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dd::decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dd::DEC_SMEM)) != cudaSuccess)
@@ -334,6 +332,9 @@ cudaError_t configure_halo_kernels() {
   if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<256, 256, 64, dd::EPI_SPLIT, true, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 dd::HaloCfg<256, 256, 64, true, true>::SMEM_BYTES)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<64, 256, 64, dd::EPI_F32_STATS, true, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                dd::HaloCfg<64, 256, 64, true, true>::SMEM_BYTES)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(dd::conv3x3_halo_kernel<256, 256, 64, dd::EPI_F32, true, true>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 dd::HaloCfg<256, 256, 64, true, true>::SMEM_BYTES)) != cudaSuccess) return e;
@@ -366,7 +367,7 @@ struct ConvLayer {
   CUtensorMap mp_hi, mp_lo;  // same, box of COUT/2 rows for the CTA-pair kernel (256-wide layers)
   __half* w_swap = nullptr;  // [9][128][CIN]: rows co = hi, 64+co = lo (swapped-operand kernel, narrow layers)
   CUtensorMap mw_swap;
-  uint8_t *w8 = nullptr, *lw8 = nullptr;  // e4m3 correction planes [9][COUT][CIN] (DD_FLAG_FP8_CORR, 256 -> 256 layers)
+  uint8_t *w8 = nullptr, *lw8 = nullptr;  // e4m3 correction planes [9][COUT][CIN] (DD_FLAG_FP8_CORR, the Cout = 256 layers)
   CUtensorMap m8_hi, m8_w, m8_lw;         // 64-channel boxes of COUT / 2 rows (fp16 hi plane, e4m3 planes): CTA-pair fp8 kernel
 };
 
@@ -490,6 +491,8 @@ constexpr int kMpChunksMax = 256;  // token chunks of the factorised attention's
 struct dd_engine {
   dd_config cfg;
   int sm_count = 0;
+  int up_vec = 4;      // DD_PROBES build: DD_UP_VEC=8 -> one warp x 8 channels per quad in gn_apply_up_split_kernel
+  bool f8_ne3 = true;  // DD_PROBES build: DD_F8_NE3=0 keeps noise_embedding.3 on the 3-pass split (A/B timing)
   unsigned long long* clk_probe = nullptr;  // DD_CLK_PROBE=1: per-launch SM cycles / nanoseconds (dd_bench_conv)
   // tuning / timing probes: read from the environment ONCE in dd_create, and only in a -DDD_PROBES build
   // (profiles/README.md); a product build ignores the variables altogether
@@ -849,7 +852,7 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
       if ((rc = make_strip_map(&ma_lo, in_lo, g.B, g.h, g.w, s.cin, hbk))) return rc;
     const bool use_pair = (e->cfg.flags & DD_FLAG_PAIR_WIDE) &&
                           (e->pair_mask >= 0 ? ((e->pair_mask >> L.sid) & 1) && s.cout == 256 : kUsePair[L.sid]);
-    if ((f8 & kF8In) && !(use_pair && L.sid == 2 && L.w8 && epi != dd::EPI_F32_STATS))
+    if ((f8 & kF8In) && !(use_pair && L.w8 && ((L.sid == 2 && epi != dd::EPI_F32_STATS) || (L.sid == 1 && epi == dd::EPI_F32_STATS))))
       return fail(DD_ERR_INVALID, "fp8-correction planes fed to a layer / kernel that does not take them");
     if ((f8 & kF8Out) && epi != dd::EPI_SPLIT) return fail(DD_ERR_INVALID, "fp8 output planes need the split epilogue");
     if (f8 & kF8In) {
@@ -858,7 +861,9 @@ int run_conv(dd_engine* e, int layer, const __half* in_hi, const __half* in_lo, 
       if ((rc = make_strip_map(&m_hi64, in_hi, g.B, g.h, g.w, s.cin, 64))) return rc;
       if ((rc = make_strip_map8(&m_a8, a8, g.B, g.h, g.w, s.cin))) return rc;
       if ((rc = make_strip_map8(&m_l8, a8 + static_cast<size_t>(g.B) * g.P * s.cin, g.B, g.h, g.w, s.cin))) return rc;
-      err = (epi == dd::EPI_SPLIT)
+      err = (L.sid == 1)
+                ? launch_pair<64, 256, 64, dd::EPI_F32_STATS, true>(m_hi64, m_a8, L.m8_hi, L.m8_w, a, e->sm_count, st, &m_l8, &L.m8_lw)
+            : (epi == dd::EPI_SPLIT)
                 ? launch_pair<256, 256, 64, dd::EPI_SPLIT, true>(m_hi64, m_a8, L.m8_hi, L.m8_w, a, e->sm_count, st, &m_l8, &L.m8_lw)
                 : launch_pair<256, 256, 64, dd::EPI_F32, true>(m_hi64, m_a8, L.m8_hi, L.m8_w, a, e->sm_count, st, &m_l8, &L.m8_lw);
     } else if (use_pair) {
@@ -956,11 +961,15 @@ int run_apply(dd_engine* e, int which, const float* temb, int temb_bstride, __ha
   }
   a.scale = kActScale;
   a.status = e->status;
-  // the tiled bilinear kernel needs the 32-pixel segment's source span to fit its 18-column staging buffer
-  // (and two consecutive output rows to touch at most three source rows: ry <= 1)
-  if (COND == 2 && C == 256 && a.rx * (dd::UPK_SEG - 1) + 2.f <= static_cast<float>(dd::UPK_SW) && a.ry <= 1.f) {
-    dim3 grid((g.w + dd::UPK_SEG - 1) / dd::UPK_SEG, (g.h + 1) / 2, g.B);
-    dd::gn_apply_up_split_kernel<<<grid, 256, dd::UPK_SMEM, st>>>(a);
+  if (COND == 2 && C == 256) {
+    // 64 threads (or one warp) per 2 x 2 output quad (rows 2i-1, 2i; columns 2j-1, 2j): grid = quad columns / 8 x quad rows x images
+    if (e->up_vec == 8) {
+      dim3 grid((g.w / 2 + 1 + 7) / 8, g.h / 2 + 1, g.B);
+      dd::gn_apply_up_split_kernel<8><<<grid, 256, 0, st>>>(a);
+    } else {
+      dim3 grid((g.w / 2 + 1 + 3) / 4, g.h / 2 + 1, g.B);
+      dd::gn_apply_up_split_kernel<4><<<grid, 256, 0, st>>>(a);
+    }
   } else {
     constexpr int PPB = 256 / (C / 8);
     dim3 grid((g.P + PPB - 1) / PPB, g.B);
@@ -979,9 +988,12 @@ int run_step(dd_engine* e, const float* temb, int temb_bstride, float cx, float 
   // noise_embedding.0 : x (16) -> 64, GN stats
   if ((rc = run_conv(e, 0, e->xs_hi, e->xs_lo, kXScale, dd::EPI_F32_STATS, e->Y, e->stats[0], nullptr, nullptr, st))) return rc;
   if ((rc = run_finalize(e, 0, 64, st))) return rc;
-  if ((rc = run_apply<64, 0>(e, 0, nullptr, 0, e->S_hi[0], e->S_lo[0], st))) return rc;
+  // with DD_FLAG_FP8_CORR noise_embedding.3 takes hi / a8 / l8 planes too (fp16 hi*hi + two e4m3 correction products)
+  const bool f8_ne3 = fp8_active(e) && e->f8_ne3;
+  if ((rc = run_apply<64, 0>(e, 0, nullptr, 0, e->S_hi[0], e->S_lo[0], st, f8_ne3))) return rc;
   // noise_embedding.3 : 64 -> 256, GN stats
-  if ((rc = run_conv(e, 1, e->S_hi[0], e->S_lo[0], kActScale, dd::EPI_F32_STATS, e->Y, e->stats[1], nullptr, nullptr, st))) return rc;
+  if ((rc = run_conv(e, 1, e->S_hi[0], e->S_lo[0], kActScale, dd::EPI_F32_STATS, e->Y, e->stats[1], nullptr, nullptr, st,
+                     f8_ne3 ? kF8In : 0))) return rc;
   if ((rc = run_finalize(e, 1, 256, st))) return rc;
   const __half *p_hi, *p_lo;
   if (e->cfg.variant == DD_VARIANT_SWIN) {
@@ -1130,7 +1142,7 @@ int pack_layer(dd_engine* e, ConvLayer& L, const float* w, const float* b, int c
     if ((rc = make_w_map(&L.mp_hi, L.w_hi, cout, cin, kHaloBK[L.sid], cout / 2))) return rc;
     if ((rc = make_w_map(&L.mp_lo, L.w_lo, cout, cin, kHaloBK[L.sid], cout / 2))) return rc;
   }
-  if (cout == 256 && cin == 256) {  // fp8-correction planes (used when the engine runs with DD_FLAG_FP8_CORR)
+  if (cout == 256 && cin % 64 == 0) {  // fp8-correction planes (used when the engine runs with DD_FLAG_FP8_CORR)
     if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.w8), n))) return rc;
     if ((rc = dev_alloc(e, reinterpret_cast<void**>(&L.lw8), n))) return rc;
     dd::pack_conv_weight8_kernel<<<128, 256, 0, st>>>(w, L.w8, L.lw8, cout, cin, scale);
@@ -1730,6 +1742,8 @@ int dd_create(const dd_config* cfg, dd_handle* out) {
   if (const char* v = getenv("DD_SWAPHALO")) e->swaphalo_mask = atoi(v);
   if (const char* v = getenv("DD_ATTN_SIMT")) e->attn_simt = atoi(v);
   e->want_clk_probe = getenv("DD_CLK_PROBE") != nullptr;
+  if (const char* v = getenv("DD_F8_NE3")) e->f8_ne3 = atoi(v) != 0;
+  if (const char* v = getenv("DD_UP_VEC")) e->up_vec = atoi(v);
 #endif
   if (cudaMallocHost(&e->status_host, 64) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -2569,7 +2583,7 @@ int dd_bench_conv(dd_handle h, int32_t cin, int32_t cout, int32_t iters, float* 
     if (h->L[i].sid >= 0 && kShapes[h->L[i].sid].cin == cin && kShapes[h->L[i].sid].cout == cout) layer = i;
   if (layer < 0) return fail(DD_ERR_UNSUPPORTED, "no packed layer with that shape in this engine variant");
   const bool split_out = (cin == 256 && cout == 256);
-  const int f8 = (split_out && fp8_active(h)) ? kF8In : 0;  // time the kernel the loop actually runs
+  const int f8 = ((split_out || (cin == 64 && cout == 256 && h->f8_ne3)) && fp8_active(h)) ? kF8In : 0;  // time the kernel the loop actually runs
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));

@@ -3,6 +3,8 @@
 // DDIM update, the fused depth-latent decoder and an fp32 CUDA-core convolution used for validation.
 // All activations are NHWC inside the engine.
 #pragma once
+#include <type_traits>
+
 #include "conv_umma.cuh"
 
 #include "ptx.cuh"
@@ -313,111 +315,187 @@ __global__ void __launch_bounds__(256) gn_apply_split_kernel(const ApplyArgs a) 
   if (ov) atomicOr(a.status, 1);
 }
 
-// Swin-head variant of the above for C = 256 with the bilinear (align_corners=True) condition injection, tiled:
-// one block = UPK_SEG consecutive output pixels of TWO consecutive latent rows.  The <= 3 x UPK_SW source pixels of the
-// condition map they interpolate from are contiguous runs in NHWC: one cp.async.bulk per source row stages them in
-// shared memory (no registers, no per-thread gather loop - a 36-iteration staging loop made the first version
-// latency-bound at 35 % of HBM bandwidth), while the threads already stream their conv outputs.  The time embedding
-// enters every tap as in the reference ((cond + te) interpolated).
-// 16-pixel segments: 3 x 10 source pixels = 31 KB of staging per block -> 6 blocks per SM.  (32-pixel segments: 57 KB, 3
-// blocks, 23 % occupancy; the kernel ran 221 us = 64 % of the copy rate either way (ncu, round 2): with 51 % issue-active
-// the bilinear + split arithmetic shares the bound with HBM.)
-constexpr int UPK_SEG = 16, UPK_SW = 10, UPK_ROWS = 3;
-constexpr int UPK_SMEM = UPK_ROWS * UPK_SW * 256 * 4 + 2 * 256 * 4 + 16;
-__global__ void __launch_bounds__(256) gn_apply_up_split_kernel(const ApplyArgs a) {
-  constexpr int C = 256, SEG = UPK_SEG, SW = UPK_SW;
-  extern __shared__ __align__(128) uint8_t upk_smem[];
-  float* sc = reinterpret_cast<float*>(upk_smem);                       // [3][SW][C]
-  float* sa = sc + UPK_ROWS * SW * C;
-  float* sb = sa + C;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sb + C);
-  const int b = blockIdx.z, oy0 = blockIdx.y * 2, ox0 = blockIdx.x * SEG;
+// Swin-head variant of the above for C = 256 with the bilinear (align_corners=True) condition injection, organised around
+// SOURCE REUSE IN REGISTERS.  ncu on the tiled versions (profiles/r02_loop_convs_ncu_full_summary.csv): DRAM traffic was
+// exactly algorithmic (548 MB read, 381 MB written) at 51 % of the DRAM peak while `l1tex__throughput` sat at 92 %: every
+// output pixel pulled its four 1 KB taps out of shared memory, 4 KB of shared-memory reads per KB of output, and neither
+// staging the conv outputs by cp.async.bulk nor a persistent three-stage ring moved it (267 -> 244 -> 246 us inside the
+// replayed graph, profiles/r02_timeline_loop*.log).  With the condition at half the latent resolution the 2 x 2 output
+// "quad" (rows 2i-1, 2i; columns 2j-1, 2j) interpolates from the SAME 2 x 2 source pixels (i-1, i) x (j-1, j).  One warp
+// (64 threads x 4 channels)
+// = one quad x 256 channels: it loads the four source pixels and its (up to) four conv outputs straight from global
+// memory into registers (16 x LDG.128 per lane in flight, coalesced 1 KB rows, no shared memory), folds the bilinear
+// weights of each output onto the quad's sources (w_rc = wy_r * wx_c; an index that is not one of the two loaded rows /
+// columns — any geometry other than exact 2x — takes the per-tap path below) and writes the operand planes.  L1 traffic
+// per output pixel: 1 KB of taps instead of 4.  Arithmetic per element ~14 instructions instead of ~25: the power-of-two
+// operand scale is folded into the GroupNorm affine, the time embedding and the weights (exact), and the time embedding
+// enters once (interp(cond + te) == interp(cond) + te * (sum of the weights), which is 1 within 2 ulp).
+
+// V (4 or 8) consecutive channels of one pixel, ALREADY multiplied by the operand scale -> planes; `mx` collects max |s|
+template <int V>
+__device__ __forceinline__ void store_planes_scaled(const float (&s)[V], __half* out_hi, __half* out_lo, uint8_t* out_a8,
+                                                    uint8_t* out_l8, size_t off, float& mx) {
+  static_assert(V == 4 || V == 8, "4 or 8 channels per thread");
+  using VH = typename std::conditional<V == 8, uint4, uint2>::type;  // V fp16 values
+  using VB = typename std::conditional<V == 8, uint2, uint32_t>::type;  // V e4m3 values
+  __align__(16) __half2 h[V / 2];
+#pragma unroll
+  for (int j = 0; j < V / 2; ++j) {
+    h[j] = __floats2half2_rn(s[2 * j], s[2 * j + 1]);
+    mx = fmaxf(mx, fmaxf(fabsf(s[2 * j]), fabsf(s[2 * j + 1])));
+  }
+  *reinterpret_cast<VH*>(out_hi + off) = *reinterpret_cast<const VH*>(h);
+  if (out_a8 != nullptr) {
+    __align__(8) uint16_t a8[V / 2];
+    __align__(8) uint16_t l8[V / 2];
+#pragma unroll
+    for (int j = 0; j < V / 2; ++j) {
+      const float2 hf = __half22float2(h[j]);
+      a8[j] = e4m3x2(s[2 * j] * kF8ActDiv, s[2 * j + 1] * kF8ActDiv);
+      l8[j] = e4m3x2((s[2 * j] - hf.x) * kF8LoMul, (s[2 * j + 1] - hf.y) * kF8LoMul);
+    }
+    *reinterpret_cast<VB*>(out_a8 + off) = *reinterpret_cast<const VB*>(a8);
+    *reinterpret_cast<VB*>(out_l8 + off) = *reinterpret_cast<const VB*>(l8);
+  } else {
+    __align__(16) __half2 l[V / 2];
+#pragma unroll
+    for (int j = 0; j < V / 2; ++j) {
+      const float2 hf = __half22float2(h[j]);
+      l[j] = __floats2half2_rn(s[2 * j] - hf.x, s[2 * j + 1] - hf.y);
+    }
+    *reinterpret_cast<VH*>(out_lo + off) = *reinterpret_cast<const VH*>(l);
+  }
+}
+
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+}
+__device__ __forceinline__ void ld4_stream(const float* p, float (&v)[4]) {
+  const float4 u = __ldcs(reinterpret_cast<const float4*>(p));
+  v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+}
+
+// ATen upsample_bilinear2d (align_corners=True) source index / weights of one output coordinate
+struct Lerp1 {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp1 lerp_coord(float ratio, int o, int n_src) {
+  Lerp1 r;
+  const float f = ratio * o;
+  r.i0 = static_cast<int>(f);
+  r.i1 = r.i0 + (r.i0 < n_src - 1 ? 1 : 0);
+  r.l1 = f - r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+// V = channels per thread (4: 64 threads per quad, 80 registers, 3 blocks per SM; 8: one warp per quad, 128 registers, 2 blocks)
+template <int V>
+__device__ __forceinline__ void ldv(const float* p, float (&v)[V]) {
+#pragma unroll
+  for (int i = 0; i < V / 4; ++i) ld4(p + 4 * i, *reinterpret_cast<float(*)[4]>(&v[4 * i]));
+}
+template <int V>
+__device__ __forceinline__ void ldv_stream(const float* p, float (&v)[V]) {
+#pragma unroll
+  for (int i = 0; i < V / 4; ++i) ld4_stream(p + 4 * i, *reinterpret_cast<float(*)[4]>(&v[4 * i]));
+}
+template <int V>
+__global__ void __launch_bounds__(256, V == 4 ? 3 : 2) gn_apply_up_split_kernel(const ApplyArgs a) {
+  constexpr int C = 256, TPQ = C / V, UPQ_QUADS = 256 / TPQ;  // threads per quad, quads per block (consecutive quad columns)
+  const int b = blockIdx.z, qy = blockIdx.y, qx = blockIdx.x * UPQ_QUADS + threadIdx.x / TPQ;
+  if (qx > a.W / 2) return;  // quad q covers output columns {2q - 1, 2q} (clipped to [0, W)): q = 0 .. W / 2
+  const int c0 = (threadIdx.x % TPQ) * V;
   const int P = a.H * a.W;
-  const int c0 = (threadIdx.x & 31) * 8;
-  const int xs = static_cast<int>(a.rx * ox0);                          // first source column of this segment
-  const int ybase = static_cast<int>(a.ry * oy0);                       // first source row
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    fence_proxy_async();
-    const int npx = min(SW, a.cw - xs);
-    const int nrow = min(UPK_ROWS, a.ch - ybase);
-    mbar_arrive_expect_tx(bar, static_cast<uint32_t>(nrow * npx * C * 4));
-    const float* base = a.cond + (static_cast<size_t>(b) * a.ch * a.cw) * C;
-    for (int r = 0; r < nrow; ++r)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       smem_u32(sc + r * SW * C)),
-                   "l"(reinterpret_cast<uint64_t>(base + (static_cast<size_t>(ybase + r) * a.cw + xs) * C)),
-                   "r"(static_cast<uint32_t>(npx * C * 4)), "r"(smem_u32(bar))
-                   : "memory");
-  }
-  float te[8];
+  const int ox[2] = {max(2 * qx - 1, 0), min(2 * qx, a.W - 1)};
+  const int oy[2] = {max(2 * qy - 1, 0), min(2 * qy, a.H - 1)};
+  const int nx = ox[1] > ox[0] ? 2 : 1, ny = oy[1] > oy[0] ? 2 : 1;
+  // the two source rows / columns this quad keeps in registers
+  const int xa = static_cast<int>(a.rx * ox[0]), xb = min(xa + 1, a.cw - 1);
+  const int ya = static_cast<int>(a.ry * oy[0]), yb = min(ya + 1, a.ch - 1);
+  const float* cbase = a.cond + static_cast<size_t>(b) * a.ch * a.cw * C + c0;
+  float S[2][2][V];
+  ldv<V>(cbase + (static_cast<size_t>(ya) * a.cw + xa) * C, S[0][0]);
+  ldv<V>(cbase + (static_cast<size_t>(ya) * a.cw + xb) * C, S[0][1]);
+  ldv<V>(cbase + (static_cast<size_t>(yb) * a.cw + xa) * C, S[1][0]);
+  ldv<V>(cbase + (static_cast<size_t>(yb) * a.cw + xb) * C, S[1][1]);
+  float Y[2][2][V];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      if (r < ny && c < nx)
+        ldv_stream<V>(a.y + (static_cast<size_t>(b) * P + static_cast<size_t>(oy[r]) * a.W + ox[c]) * C + c0, Y[r][c]);
+  // per-image constants of this thread's channels, pre-multiplied by the (power-of-two) operand scale
+  float sa[V], sb[V], te[V];
   {
-    const float4 t0 = *reinterpret_cast<const float4*>(a.temb + static_cast<size_t>(b) * a.temb_bstride + c0);
-    const float4 t1 = *reinterpret_cast<const float4*>(a.temb + static_cast<size_t>(b) * a.temb_bstride + c0 + 4);
-    te[0] = t0.x; te[1] = t0.y; te[2] = t0.z; te[3] = t0.w; te[4] = t1.x; te[5] = t1.y; te[6] = t1.z; te[7] = t1.w;
-  }
-  {
-    const int c = threadIdx.x;
-    const int g = c / (C / 4);
+    const int g = c0 / (C / 4);
     const float mean = a.mean_rstd[(b * 4 + g) * 2], rstd = a.mean_rstd[(b * 4 + g) * 2 + 1];
-    const float scl = rstd * a.gamma[c];
-    sa[c] = scl;
-    sb[c] = a.beta[c] - scl * mean;
-  }
-  __syncthreads();  // sa / sb, and the barrier init is visible to the waiters
-  bool ov = false;
-  bool staged = false;
-#pragma unroll 1
-  for (int rr = 0; rr < 2; ++rr) {
-    const int oy = oy0 + rr;
-    if (oy >= a.H) break;
-    // this thread's conv outputs of the row: 4 pixels x 8 channels, all loads in flight before the first use
-    float4 u[SEG / 8][2];
+    float gm[V], bt[V], tt[V];
+    ldv<V>(a.gamma + c0, gm);
+    ldv<V>(a.beta + c0, bt);
+    ldv<V>(a.temb + static_cast<size_t>(b) * a.temb_bstride + c0, tt);
 #pragma unroll
-    for (int k = 0; k < SEG / 8; ++k) {
-      const int ox = ox0 + (threadIdx.x >> 5) + 8 * k;
-      if (ox < a.W) {
-        const size_t off = (static_cast<size_t>(b) * P + static_cast<size_t>(oy) * a.W + ox) * C + c0;
-        u[k][0] = __ldcs(reinterpret_cast<const float4*>(a.y + off));
-        u[k][1] = __ldcs(reinterpret_cast<const float4*>(a.y + off + 4));
-      } else {
-        u[k][0] = u[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    if (!staged) {
-      mbar_wait(bar, 0);
-      staged = true;
-    }
-    const float fy = a.ry * oy;
-    const int y0 = static_cast<int>(fy);
-    const int y1 = y0 + (y0 < a.ch - 1 ? 1 : 0);
-    const float ly1 = fy - y0, ly0 = 1.f - ly1;
-    const float* r0 = sc + (y0 - ybase) * SW * C;
-    const float* r1 = sc + (y1 - ybase) * SW * C;
-#pragma unroll
-    for (int k = 0; k < SEG / 8; ++k) {
-      const int ox = ox0 + (threadIdx.x >> 5) + 8 * k;
-      if (ox >= a.W) continue;
-      const size_t off = (static_cast<size_t>(b) * P + static_cast<size_t>(oy) * a.W + ox) * C + c0;
-      const float v[8] = {u[k][0].x, u[k][0].y, u[k][0].z, u[k][0].w, u[k][1].x, u[k][1].y, u[k][1].z, u[k][1].w};
-      const float fx = a.rx * ox;
-      const int x0 = static_cast<int>(fx);
-      const int x1 = x0 + (x0 < a.cw - 1 ? 1 : 0);
-      const float lx1 = fx - x0, lx0 = 1.f - lx1;
-      const int i0 = (x0 - xs) * C + c0, i1 = (x1 - xs) * C + c0;
-      float o8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gn = fmaxf(fmaf(v[j], sa[c0 + j], sb[c0 + j]), 0.f);
-        // (cond + te) interpolated exactly as the reference does it: te enters every tap
-        const float up = ly0 * (lx0 * (r0[i0 + j] + te[j]) + lx1 * (r0[i1 + j] + te[j])) +
-                         ly1 * (lx0 * (r1[i0 + j] + te[j]) + lx1 * (r1[i1 + j] + te[j]));
-        o8[j] = up + gn;
-      }
-      store_planes8(o8, a.scale, a.out_hi, a.out_lo, a.out_a8, a.out_l8, off, ov);
+    for (int j = 0; j < V; ++j) {
+      const float scl = rstd * gm[j];  // same rounding as the generic kernel: (rstd * gamma), beta - that * mean
+      sa[j] = scl * a.scale;
+      sb[j] = (bt[j] - scl * mean) * a.scale;
+      te[j] = tt[j] * a.scale;
     }
   }
-  if (ov) atomicOr(a.status, 1);
+  float mx = 0.f;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (r >= ny) break;
+    const Lerp1 ly = lerp_coord(a.ry, oy[r], a.ch);
+    const bool oky = (ly.i0 == ya || ly.i0 == yb) && (ly.i1 == ya || ly.i1 == yb);
+    // weights of the two loaded source rows (a clamped pair ya == yb puts everything on row a)
+    const float wya = (ly.i0 == ya ? ly.l0 : 0.f) + (ly.i1 == ya ? ly.l1 : 0.f);
+    const float wyb = yb != ya ? (ly.i0 == yb ? ly.l0 : 0.f) + (ly.i1 == yb ? ly.l1 : 0.f) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      if (c >= nx) break;
+      const Lerp1 lx = lerp_coord(a.rx, ox[c], a.cw);
+      const bool ok = oky && (lx.i0 == xa || lx.i0 == xb) && (lx.i1 == xa || lx.i1 == xb);
+      float sv[V];
+      if (ok) {
+        const float wxa = (lx.i0 == xa ? lx.l0 : 0.f) + (lx.i1 == xa ? lx.l1 : 0.f);
+        const float wxb = xb != xa ? (lx.i0 == xb ? lx.l0 : 0.f) + (lx.i1 == xb ? lx.l1 : 0.f) : 0.f;
+        const float w00 = wya * wxa * a.scale, w01 = wya * wxb * a.scale, w10 = wyb * wxa * a.scale, w11 = wyb * wxb * a.scale;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float gn = fmaxf(fmaf(Y[r][c][j], sa[j], sb[j]), 0.f);
+          float up = fmaf(w00, S[0][0][j], te[j]);
+          up = fmaf(w01, S[0][1][j], up);
+          up = fmaf(w10, S[1][0][j], up);
+          up = fmaf(w11, S[1][1][j], up);
+          sv[j] = up + gn;
+        }
+      } else {  // geometry other than 2x: this output's taps are not the quad's sources — fetch them
+        float q00[V], q01[V], q10[V], q11[V];
+        ldv<V>(cbase + (static_cast<size_t>(ly.i0) * a.cw + lx.i0) * C, q00);
+        ldv<V>(cbase + (static_cast<size_t>(ly.i0) * a.cw + lx.i1) * C, q01);
+        ldv<V>(cbase + (static_cast<size_t>(ly.i1) * a.cw + lx.i0) * C, q10);
+        ldv<V>(cbase + (static_cast<size_t>(ly.i1) * a.cw + lx.i1) * C, q11);
+        const float w00 = ly.l0 * lx.l0 * a.scale, w01 = ly.l0 * lx.l1 * a.scale, w10 = ly.l1 * lx.l0 * a.scale,
+                    w11 = ly.l1 * lx.l1 * a.scale;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float gn = fmaxf(fmaf(Y[r][c][j], sa[j], sb[j]), 0.f);
+          float up = fmaf(w00, q00[j], te[j]);
+          up = fmaf(w01, q01[j], up);
+          up = fmaf(w10, q10[j], up);
+          up = fmaf(w11, q11[j], up);
+          sv[j] = up + gn;
+        }
+      }
+      const size_t off = (static_cast<size_t>(b) * P + static_cast<size_t>(oy[r]) * a.W + ox[c]) * C + c0;
+      store_planes_scaled<V>(sv, a.out_hi, a.out_lo, a.out_a8, a.out_l8, off, mx);
+    }
+  }
+  if (mx > (a.out_a8 != nullptr ? kF8ActMax : 60000.f)) atomicOr(a.status, 1);
 }
 
 // ------------------------------------------------------------------ last GN + ReLU (C = 16) fused with the DDIM update

@@ -68,9 +68,10 @@ gaps = collections.OrderedDict()
 for i, e in enumerate(ev):
     n = re.sub(r"\(.*", "", e["name"])
     n = re.sub(r"^void |dd::", "", n)[:70]
-    a = agg.setdefault(n, [0, 0.0])
+    a = agg.setdefault(n, [0, 0.0, []])
     a[0] += 1
     a[1] += e["dur"]
+    a[2].append(e["dur"])
     if i + 1 < len(ev):
         gp = gaps.setdefault(n, [0, 0.0])
         gp[0] += 1
@@ -79,10 +80,17 @@ out = {"kernels": len(ev), "span_us": span, "busy_us": busy, "idle_us": span - b
        "T": T, "full_forward": full, "per_kernel": []}
 print(f"{len(ev)} kernels in one replay: span {span/1e3:.2f} ms, kernels {busy/1e3:.2f} ms, between kernels {(span-busy)/1e3:.2f} ms "
       f"({100*(span-busy)/span:.1f} %)")
-for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+for n, (c, t, durs) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     gc, gt = gaps.get(n, [0, 0.0])
-    out["per_kernel"].append({"kernel": n, "launches": c, "total_us": t, "mean_us": t / c, "gap_after_mean_us": gt / max(gc, 1)})
-    print(f"{c:5d} x {t/c:8.1f} us = {t/1e3:8.2f} ms   gap after: {gt/max(gc,1):6.1f} us   {n}")
+    sd = sorted(durs)
+    med = sd[len(sd) // 2]
+    # launches of one name alternate between call sites inside a step (convA / convB, the two 64-channel GN-apply passes)
+    even = sorted(durs[0::2])
+    odd = sorted(durs[1::2]) or [0.0]
+    out["per_kernel"].append({"kernel": n, "launches": c, "total_us": t, "mean_us": t / c, "median_us": med, "min_us": sd[0],
+                              "max_us": sd[-1], "median_even_us": even[len(even) // 2], "median_odd_us": odd[len(odd) // 2],
+                              "gap_after_mean_us": gt / max(gc, 1)})
+    print(f"{c:5d} x {t/c:8.1f} us = {t/1e3:8.2f} ms  med {med:7.1f} min {sd[0]:7.1f} max {sd[-1]:7.1f} even/odd {even[len(even)//2]:7.1f}/{odd[len(odd)//2]:7.1f}  {n}")
 dst = os.environ.get("DD_OUT")
 if dst:
     json.dump(out, open(dst, "w"), indent=1)
