@@ -343,7 +343,7 @@ def main():
             parity = {"case": GOLDEN_OF[args.workload], "against": f"real reference forward (golden, logits sub-sampled x{st})",
                       "max_dz": dz.max().item(), "rms_dz": dz.pow(2).mean().sqrt().item(), "tolerance": 1e-3,
                       "what": "|dz| on the decoder logit == relative depth error", "n": dz.numel(),
-                      "mode": "exact 3-pass fp16 split" if args.exact else "fp8 correction products on convA/convB"}
+                      "mode": "exact 3-pass fp16 split" if args.exact else "fp8 correction products on convA / convB / noise_embedding.3"}
 
     # roofline of the dominant kernel: the 256->256 3x3 conv (convA/convB = 79 % of the loop's FLOPs)
     pk = peaks()
@@ -387,7 +387,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": ("f32 (fp32-grade products on tcgen05: 3-pass fp16 split, fp32 accumulate in TMEM" +
-                      (")" if args.exact or family != "swinl" else "; convA/convB: fp16 hi*hi + two e4m3 correction products)")),
+                      (")" if args.exact or family != "swinl" else "; convA / convB / noise_embedding.3: fp16 hi*hi + two e4m3 correction products)")),
             "data": "synthetic",
             "config": cfg, "clocks": clocks, "gpu_launches": launches, "parity": parity,
             "per_rank_ms_per_step": per_rank or None, "per_rank_output_mean": rank_means,

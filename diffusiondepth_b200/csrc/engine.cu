@@ -386,6 +386,8 @@ struct GenLayer {
   float wscale = 1.f;
   CUtensorMap mb_hi, mb_lo;
   CUtensorMap mp_hi, mp_lo;  // box of nt / 2 rows: each CTA of a pair stages half of the N tile
+  bool alt = false;          // cout divisible by 256 and 192: run_gen picks the width whose last wave wastes least
+  CUtensorMap mb_hi_alt, mb_lo_alt, mp_hi_alt, mp_lo_alt;  // boxes of 192 / 96 rows
 };
 struct Planes {
   __half* hi = nullptr;
@@ -491,7 +493,7 @@ constexpr int kMpChunksMax = 256;  // token chunks of the factorised attention's
 struct dd_engine {
   dd_config cfg;
   int sm_count = 0;
-  int up_vec = 4;      // DD_PROBES build: DD_UP_VEC=8 -> one warp x 8 channels per quad in gn_apply_up_split_kernel
+  int up_qpb = 4;      // quads per block in gn_apply_up_split_kernel; DD_PROBES build: DD_UP_QPB=1 -> one 64-thread block per quad (A/B: equal)
   bool f8_ne3 = true;  // DD_PROBES build: DD_F8_NE3=0 keeps noise_embedding.3 on the 3-pass split (A/B timing)
   unsigned long long* clk_probe = nullptr;  // DD_CLK_PROBE=1: per-launch SM cycles / nanoseconds (dd_bench_conv)
   // tuning / timing probes: read from the environment ONCE in dd_create, and only in a -DDD_PROBES build
@@ -962,13 +964,13 @@ int run_apply(dd_engine* e, int which, const float* temb, int temb_bstride, __ha
   a.scale = kActScale;
   a.status = e->status;
   if (COND == 2 && C == 256) {
-    // 64 threads (or one warp) per 2 x 2 output quad (rows 2i-1, 2i; columns 2j-1, 2j): grid = quad columns / 8 x quad rows x images
-    if (e->up_vec == 8) {
-      dim3 grid((g.w / 2 + 1 + 7) / 8, g.h / 2 + 1, g.B);
-      dd::gn_apply_up_split_kernel<8><<<grid, 256, 0, st>>>(a);
-    } else {
+    // one 64-thread block per 2 x 2 output quad (rows 2i-1, 2i; columns 2j-1, 2j)
+    if (e->up_qpb == 4) {
       dim3 grid((g.w / 2 + 1 + 3) / 4, g.h / 2 + 1, g.B);
-      dd::gn_apply_up_split_kernel<4><<<grid, 256, 0, st>>>(a);
+      dd::gn_apply_up_split_kernel<4, 4><<<grid, 256, 0, st>>>(a);
+    } else {
+      dim3 grid(g.w / 2 + 1, g.h / 2 + 1, g.B);
+      dd::gn_apply_up_split_kernel<4, 1><<<grid, 64, 0, st>>>(a);
     }
   } else {
     constexpr int PPB = 256 / (C / 8);
@@ -1254,6 +1256,13 @@ int pack_gen(dd_engine* e, GenLayer& L, const std::string& wkey, const std::stri
   if ((rc = make_wgen_map(&L.mb_lo, L.w_lo, L.cout, cp, L.taps, L.nt))) return rc;
   if ((rc = make_wgen_map(&L.mp_hi, L.w_hi, L.cout, cp, L.taps, L.nt / 2))) return rc;
   if ((rc = make_wgen_map(&L.mp_lo, L.w_lo, L.cout, cp, L.taps, L.nt / 2))) return rc;
+  L.alt = (L.nt == 256 && L.cout % 256 == 0 && L.cout % 192 == 0 && !L.shuffle);
+  if (L.alt) {
+    if ((rc = make_wgen_map(&L.mb_hi_alt, L.w_hi, L.cout, cp, L.taps, 192))) return rc;
+    if ((rc = make_wgen_map(&L.mb_lo_alt, L.w_lo, L.cout, cp, L.taps, 192))) return rc;
+    if ((rc = make_wgen_map(&L.mp_hi_alt, L.w_hi, L.cout, cp, L.taps, 96))) return rc;
+    if ((rc = make_wgen_map(&L.mp_lo_alt, L.w_lo, L.cout, cp, L.taps, 96))) return rc;
+  }
   return DD_OK;
 }
 
@@ -1335,7 +1344,16 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
   a.tiles_x = (W + dd::TILE_W - 1) / dd::TILE_W;
   a.tiles_y = (H + dd::TILE_H - 1) / dd::TILE_H;
   a.m_tiles = a.tiles_x * a.tiles_y * B;
-  a.n_tiles = (L.cout + L.nt - 1) / L.nt;
+  // wave quantisation (as in run_gemm): with few M tiles pick the N-tile width whose last wave wastes least — the
+  // level-2 fusion conv of the HAHI neck (768 channels, 30 tile pairs) runs 2 waves of 192 columns instead of 2 of 256
+  const bool pair = gen_use_pair(e, a.m_tiles);
+  int nt = L.nt;
+  if (L.alt) {
+    const int units = pair ? (a.m_tiles + 1) / 2 : a.m_tiles, slots = pair ? e->sm_count / 2 : e->sm_count;
+    auto cost = [&](int w) { return ((units * (L.cout / w) + slots - 1) / slots) * w; };
+    if (cost(192) < cost(256)) nt = 192;
+  }
+  a.n_tiles = (L.cout + nt - 1) / nt;
   a.kc0 = (c0 + dd::GEN_BK - 1) / dd::GEN_BK;  // a partial last chunk is zero-filled by TMA on both operands
   a.kc1 = (c1 + dd::GEN_BK - 1) / dd::GEN_BK;
   a.c0_ch = c0;
@@ -1373,10 +1391,11 @@ int run_gen(dd_engine* e, const GenLayer& L, const Planes& a0, int c0, const Pla
     m1h = m0h;
     m1l = m0l;
   }
-  const bool pair = gen_use_pair(e, a.m_tiles);
   const int grid = gen_grid(e, pair, a.m_tiles, a.n_tiles);
-  const cudaError_t err = launch_gen_nt(L.nt, pair, grid, st, m0h, m0l, m1h, m1l, pair ? L.mp_hi : L.mb_hi,
-                                        pair ? L.mp_lo : L.mb_lo, a);
+  const bool use_alt = nt != L.nt;
+  const cudaError_t err = launch_gen_nt(nt, pair, grid, st, m0h, m0l, m1h, m1l,
+                                        pair ? (use_alt ? L.mp_hi_alt : L.mp_hi) : (use_alt ? L.mb_hi_alt : L.mb_hi),
+                                        pair ? (use_alt ? L.mp_lo_alt : L.mp_lo) : (use_alt ? L.mb_lo_alt : L.mb_lo), a);
   e->launches++;
   if (err != cudaSuccess) return fail(DD_ERR_CUDA, std::string("convgen launch: ") + cudaGetErrorString(err));
   return DD_OK;
@@ -1743,7 +1762,7 @@ int dd_create(const dd_config* cfg, dd_handle* out) {
   if (const char* v = getenv("DD_ATTN_SIMT")) e->attn_simt = atoi(v);
   e->want_clk_probe = getenv("DD_CLK_PROBE") != nullptr;
   if (const char* v = getenv("DD_F8_NE3")) e->f8_ne3 = atoi(v) != 0;
-  if (const char* v = getenv("DD_UP_VEC")) e->up_vec = atoi(v);
+  if (const char* v = getenv("DD_UP_QPB")) e->up_qpb = atoi(v);
 #endif
   if (cudaMallocHost(&e->status_host, 64) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -391,7 +391,11 @@ __device__ __forceinline__ Lerp1 lerp_coord(float ratio, int o, int n_src) {
   return r;
 }
 
-// V = channels per thread (4: 64 threads per quad, 80 registers, 3 blocks per SM; 8: one warp per quad, 128 registers, 2 blocks)
+// V = channels per thread (4: 64 threads per quad, 80 registers, 3 blocks of 256 threads per SM).  Measured variants that
+// changed nothing inside the graph (profiles/README.md, session 2): 8 channels per thread / one warp per quad (128
+// registers, 2 blocks: 214.5 vs 214.5 us, and convA behind it 30 us slower), one quad per 64-thread block so that the
+// quad's scalars are warp-uniform (189-216 vs 201-220 us).  ncu at 1.89 GHz: 185 us, DRAM 61 % of its peak, issue-active
+// 72 %, ALU pipe 57 %: at the power-capped clock of the replayed graph the kernel is issue-bound on its per-quad scalar work.
 template <int V>
 __device__ __forceinline__ void ldv(const float* p, float (&v)[V]) {
 #pragma unroll
@@ -402,11 +406,12 @@ __device__ __forceinline__ void ldv_stream(const float* p, float (&v)[V]) {
 #pragma unroll
   for (int i = 0; i < V / 4; ++i) ld4_stream(p + 4 * i, *reinterpret_cast<float(*)[4]>(&v[4 * i]));
 }
-template <int V>
-__global__ void __launch_bounds__(256, V == 4 ? 3 : 2) gn_apply_up_split_kernel(const ApplyArgs a) {
-  constexpr int C = 256, TPQ = C / V, UPQ_QUADS = 256 / TPQ;  // threads per quad, quads per block (consecutive quad columns)
-  const int b = blockIdx.z, qy = blockIdx.y, qx = blockIdx.x * UPQ_QUADS + threadIdx.x / TPQ;
-  if (qx > a.W / 2) return;  // quad q covers output columns {2q - 1, 2q} (clipped to [0, W)): q = 0 .. W / 2
+template <int V, int QPB>  // QPB quads (consecutive quad columns) per block of QPB * 256 / V threads
+__global__ void __launch_bounds__(QPB * 256 / V, 12 / QPB) gn_apply_up_split_kernel(const ApplyArgs a) {
+  constexpr int C = 256, TPQ = C / V;
+  const int b = blockIdx.z, qy = blockIdx.y;
+  const int qx = QPB == 1 ? blockIdx.x : blockIdx.x * QPB + threadIdx.x / TPQ;  // quad q: output columns {2q - 1, 2q} in [0, W)
+  if (QPB > 1 && qx > a.W / 2) return;
   const int c0 = (threadIdx.x % TPQ) * V;
   const int P = a.H * a.W;
   const int ox[2] = {max(2 * qx - 1, 0), min(2 * qx, a.W - 1)};

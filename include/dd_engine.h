@@ -70,7 +70,8 @@ enum dd_flags {
   DD_FLAG_SWAP_NARROW = 1 << 4, /* Cout <= 64 convs on the swapped-operand kernel (weights as A, 256 pixels as N) */
   DD_FLAG_PAIR_WIDE = 1 << 5,   /* Cout = 256 convs on CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256) */
   DD_FLAG_STEP_DECODE = 1 << 6, /* reserve workspace for dd_denoise_decode_steps (T decoded maps; the *Vis heads) */
-  DD_FLAG_FP8_CORR = 1 << 7     /* Swin variant, with HALO_CONV | PAIR_WIDE: the two 256->256 convs compute the correction
+  DD_FLAG_FP8_CORR = 1 << 7     /* Swin variant, with HALO_CONV | PAIR_WIDE: the Cout = 256 convs (convA, convB 256->256 and
+                                   noise_embedding.3 64->256) compute the correction
                                    products of the split (x_lo * w_hi, x_hi * w_lo) as e4m3 MMAs (kind::f8f6f4, K = 32) and
                                    only hi * hi in fp16: 2 pass-equivalents instead of 3, ~1.5x on the dominant kernel.
                                    Error per product ~2^-15 instead of ~2^-22 (DESIGN.md "Numerics": max |dz| 3.4e-4 on

@@ -91,6 +91,13 @@ for n, (c, t, durs) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                               "max_us": sd[-1], "median_even_us": even[len(even) // 2], "median_odd_us": odd[len(odd) // 2],
                               "gap_after_mean_us": gt / max(gc, 1)})
     print(f"{c:5d} x {t/c:8.1f} us = {t/1e3:8.2f} ms  med {med:7.1f} min {sd[0]:7.1f} max {sd[-1]:7.1f} even/odd {even[len(even)//2]:7.1f}/{odd[len(odd)//2]:7.1f}  {n}")
+if os.environ.get("DD_DUMP"):
+    # every launch of the replay in order: duration, grid, block, name (CUPTI's launch record)
+    with open(os.environ["DD_DUMP"], "w") as f:
+        for i, e in enumerate(ev):
+            ar = e.get("args", {})
+            f.write(f"{i:4d} {e['dur']:9.1f} us  grid {ar.get('grid')} block {ar.get('block')}  "
+                    f"{re.sub(r'^void |dd::', '', re.sub(r'[(].*', '', e['name']))[:90]}\n")
 dst = os.environ.get("DD_OUT")
 if dst:
     json.dump(out, open(dst, "w"), indent=1)
