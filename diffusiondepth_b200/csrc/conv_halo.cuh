@@ -69,12 +69,23 @@ struct HaloCfg {
   // set then owns two GroupNorm groups) and the pair kernel's 64->256 layer (K = 576: 18 stages per tile, so draining a
   // 128 x 256 fp32 tile with one warp per scheduler took as long as the mainloop; the sets take alternate chunks and
   // each holds partial sums of all four groups).
-  static constexpr int EPI_SETS = (COUT == 64 || PAIR) ? 2 : 1;
+  // F8_NARROW_K (64 -> 256 with fp8 corrections: nine stages of 2 pass-equivalents per tile): FOUR sets on 16-column
+  // chunks (16 epilogue warps, <= 96 registers).  ncu with two sets: tensor pipe 62 % active, issue-active 41 % with two
+  // epilogue warps per scheduler stalled on their own TMEM / shared-memory latencies — the drain of a 128 x 256 fp32
+  // tile, not the mainloop, set the tile rate.
+#ifdef DD_NE3_EPI8  // A/B build of profiles/README.md (session 2): the two-set epilogue on 32-column chunks
+  static constexpr bool F8_EPI16 = false;
+#else
+  static constexpr bool F8_EPI16 = F8_NARROW_K;
+#endif
+  static constexpr int EPI_SETS = F8_EPI16 ? 4 : ((COUT == 64 || PAIR) ? 2 : 1);
   static constexpr bool STATS_LOCAL = (COUT == 64);  // a set's chunk(s) cover whole groups of their own
   static constexpr int EPI_WARPS = 4 * EPI_SETS;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
-  static constexpr int XPOSE_BYTES = (F8 && !F8_NARROW_K) ? 0 : EPI_WARPS * 32 * 32 * 4;  // F8 256 -> 256: fp32 outputs (tests) store row-wise
-  static constexpr int BUDGET = 227 * 1024 - 1024 - 1024 - XPOSE_BYTES - A_SLOTS * A_SLOT;
+  static constexpr int CH = COUT < 32 ? COUT : (F8_EPI16 ? 16 : 32);  // accumulator columns per epilogue chunk
+  static constexpr int XPOSE_BYTES = (F8 && !F8_NARROW_K) ? 0 : EPI_WARPS * 32 * CH * 4;  // F8 256 -> 256: fp32 outputs (tests) store row-wise
+  static constexpr int CTRL_BYTES = EPI_WARPS > 8 ? 2048 : 1024;  // barriers, TMEM slot, GroupNorm partials [2][EPI_WARPS][4][2]
+  static constexpr int BUDGET = 227 * 1024 - 1024 - CTRL_BYTES - XPOSE_BYTES - A_SLOTS * A_SLOT;
   static constexpr int B_SLOTS_RAW = BUDGET / B_SLOT;
   // Small layers (16->64, 64->16): all 9 x KC weight tiles fit in shared memory -> fetch them ONCE per CTA instead of once
   // per tile.  Each cp.async.bulk.tensor costs its issuing thread ~160 ns, and 18 weight copies per 128-pixel tile were
@@ -83,7 +94,7 @@ struct HaloCfg {
   static constexpr int B_SLOTS = B_RESIDENT ? 9 * KC : (F8 ? 3 : (B_SLOTS_RAW > 8 ? 8 : B_SLOTS_RAW));
   static_assert(!F8 || B_SLOTS_RAW >= 3, "fp8 layout does not fit");
   static_assert(B_SLOTS >= 2, "B ring too small");
-  static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + 1024 + XPOSE_BYTES;
+  static constexpr int SMEM_BYTES = A_SLOTS * A_SLOT + B_SLOTS * B_SLOT + 1024 + CTRL_BYTES + XPOSE_BYTES;
   static constexpr int A_TX = F8 ? STRIP_BYTES + 2 * STRIP8_BYTES : 6 * STRIP_BYTES;
   static constexpr int B_TX = F8 ? B_TILE + 2 * B8_TILE : 2 * B_TILE;
   // Narrow-N layers: back-to-back MMAs into ONE accumulator serialise on its read-modify-write latency (~105 cycles
@@ -93,7 +104,6 @@ struct HaloCfg {
   static constexpr int ACC_COLS = NACC * COUT;  // TMEM columns per accumulator buffer
   static constexpr int TMEM_COLS_RAW = 2 * ACC_COLS;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : (TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512)));
-  static constexpr int CH = COUT < 32 ? COUT : 32;
   static constexpr int GROUP_CH = COUT / 4;
 };
 
@@ -120,7 +130,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [2][4][4][2]
-  float* xpose = reinterpret_cast<float*>(ctrl + 1024);
+  float* xpose = reinterpret_cast<float*>(ctrl + C::CTRL_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -456,7 +466,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int r = m >> 3, c = m & 7;
     uint32_t full_phase = 0;
     int buf = 0, par = 0;
-    float* T = xpose + (es * 4 + q) * 1024;
+    float* T = xpose + (es * 4 + q) * (32 * C::CH);
     long long clk0 = 0;
     unsigned long long ns0 = 0;
     const bool probe = p.clk_probe != nullptr && blockIdx.x == 0 && threadIdx.x == 128;
@@ -516,7 +526,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             }
           }
         }
-        if constexpr ((EPI == EPI_F32_STATS || EPI == EPI_F32) && C::CH == 32 && C::XPOSE_BYTES > 0) {
+        if constexpr ((EPI == EPI_F32_STATS || EPI == EPI_F32) && C::CH == 16 && C::XPOSE_BYTES > 0) {
+          // [32 px][16 ch] re-distribution tile (XOR-swizzled): each store instruction writes the 64-byte segments of two
+          // pixel rows (lanes 0..15: row 2i, lanes 16..31: row 2i + 1)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) T[lane * 16 + ((j ^ lane) & 15)] = v[j];
+          __syncwarp();
+          const int hsel = lane >> 4, cl = lane & 15;
+#pragma unroll 8
+          for (int i = 0; i < 16; ++i) {
+            const int rw = 2 * i + hsel;
+            const uint32_t o = __shfl_sync(0xffffffffu, row_off, rw) + ch0 + cl;
+            if ((vmask >> rw) & 1u) p.y32[o] = T[rw * 16 + ((cl ^ rw) & 15)];
+          }
+          __syncwarp();
+        } else if constexpr ((EPI == EPI_F32_STATS || EPI == EPI_F32) && C::CH == 32 && C::XPOSE_BYTES > 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) T[lane * 32 + ((j ^ lane) & 31)] = v[j];
           __syncwarp();
@@ -605,7 +629,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           }
         }
         if constexpr (C::EPI_SETS == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 1, 256;" ::: "memory");
+        else if constexpr (C::EPI_SETS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 1, 512;" ::: "memory");
         const int e = threadIdx.x - 128;
         if (e < 8 && tile < p.num_tiles) {
           const int g = e >> 1, which = e & 1;
