@@ -197,6 +197,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     model = dd_helpers.build_mirror(family, T).to(dev)
     model.depth_head.use_cuda_graph = not args.no_graph

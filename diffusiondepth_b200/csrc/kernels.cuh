@@ -316,20 +316,19 @@ __global__ void __launch_bounds__(256) gn_apply_split_kernel(const ApplyArgs a) 
 }
 
 // Swin-head variant of the above for C = 256 with the bilinear (align_corners=True) condition injection, organised around
-// SOURCE REUSE IN REGISTERS.  ncu on the tiled versions (profiles/r02_loop_convs_ncu_full_summary.csv): DRAM traffic was
-// exactly algorithmic (548 MB read, 381 MB written) at 51 % of the DRAM peak while `l1tex__throughput` sat at 92 %: every
+// SOURCE REUSE IN REGISTERS.  ncu on the tiled versions (profiles/r02_loop_convs_ncu_full_summary_session1.csv): DRAM traffic
+// was exactly algorithmic (548 MB read, 381 MB written) at 51 % of the DRAM peak while `l1tex__throughput` sat at 92 %: every
 // output pixel pulled its four 1 KB taps out of shared memory, 4 KB of shared-memory reads per KB of output, and neither
 // staging the conv outputs by cp.async.bulk nor a persistent three-stage ring moved it (267 -> 244 -> 246 us inside the
-// replayed graph, profiles/r02_timeline_loop*.log).  With the condition at half the latent resolution the 2 x 2 output
-// "quad" (rows 2i-1, 2i; columns 2j-1, 2j) interpolates from the SAME 2 x 2 source pixels (i-1, i) x (j-1, j).  One warp
-// (64 threads x 4 channels)
-// = one quad x 256 channels: it loads the four source pixels and its (up to) four conv outputs straight from global
-// memory into registers (16 x LDG.128 per lane in flight, coalesced 1 KB rows, no shared memory), folds the bilinear
-// weights of each output onto the quad's sources (w_rc = wy_r * wx_c; an index that is not one of the two loaded rows /
-// columns — any geometry other than exact 2x — takes the per-tap path below) and writes the operand planes.  L1 traffic
-// per output pixel: 1 KB of taps instead of 4.  Arithmetic per element ~14 instructions instead of ~25: the power-of-two
-// operand scale is folded into the GroupNorm affine, the time embedding and the weights (exact), and the time embedding
-// enters once (interp(cond + te) == interp(cond) + te * (sum of the weights), which is 1 within 2 ulp).
+// replayed graph, profiles/README.md "Round 2, session 2").  With the condition at half the latent resolution the 2 x 2 output
+// "quad" (rows 2i-1, 2i; columns 2j-1, 2j) interpolates from the SAME 2 x 2 source pixels (i-1, i) x (j-1, j).  64 threads x
+// 4 channels = one quad x 256 channels: they load the four source pixels and the quad's (up to) four conv outputs straight
+// from global memory into registers (8 x LDG.128 per thread in flight, coalesced 1 KB rows, no shared memory), fold the
+// bilinear weights of each output onto the quad's sources (w_rc = wy_r * wx_c; an index that is not one of the two loaded
+// rows / columns — any geometry other than exact 2x — takes the per-tap path below) and write the operand planes.  L1
+// traffic per output pixel: 1 KB of taps instead of 4.  The power-of-two operand scale is folded into the GroupNorm affine,
+// the time embedding and the weights (exact), and the time embedding enters once (interp(cond + te) == interp(cond) + te *
+// (sum of the weights), which is 1 within 2 ulp).
 
 // V (4 or 8) consecutive channels of one pixel, ALREADY multiplied by the operand scale -> planes; `mx` collects max |s|
 template <int V>
