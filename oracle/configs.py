@@ -46,6 +46,10 @@ GOLDEN_TRAINED = {
     "g_swinl_small_trained": ("swinl", 5, 1, 96, 160),
     "g_res18_trained": ("res18", 5, 2, 70, 106),
     "g_mpvit_trained": ("mpvit_s", 5, 2, 70, 106),  # odd sizes on every MPViT level (35x53 .. 5x7), folded BN everywhere
+    # Swin head on an odd image: patch embed pads 70x106 -> 72x108, condition map 18x27 under a 35x53 latent (align_corners
+    # ratio exactly 0.5 but NOT the 2x layout: half of the outputs of the quad-based condition-injection kernel take their
+    # per-tap path), every pyramid level odd (18x27, 9x14, 5x7, 3x4: resampling FPN, padded + shifted windows)
+    "g_swinl_odd_trained": ("swinl", 5, 2, 70, 106),
 }
 SEED_TRAINED = 99
 

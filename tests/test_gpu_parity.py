@@ -369,7 +369,7 @@ def _run_plugin(case, batch=None, fp8=True):
 
 @pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_swinl_small", "g_res50_c2", "g_swinl_c3",
                                   "g_swinl_c5", "g_swinl_add_small", "g_mpvit_small", "g_mpvit_trained", "g_res18_trained",
-                                  "g_swinl_small_trained"])
+                                  "g_swinl_small_trained", "g_swinl_odd_trained"])
 def test_plugin_forward_matches_reference_golden(case, parity_log):
     """`Diffusion_DCbase_Model.forward(sample)` on the GPU vs the real reference's own forward (golden).  `*_trained`:
     the trained-like regime (non-zero Swin relative-position tables, non-trivial BN statistics, LN / GN affines)."""
@@ -399,7 +399,7 @@ def test_plugin_forward_matches_reference_golden(case, parity_log):
         assert out[k] is None
 
 
-@pytest.mark.parametrize("case", ["g_swinl_small", "g_swinl_c3", "g_swinl_c5", "g_swinl_small_trained"])
+@pytest.mark.parametrize("case", ["g_swinl_small", "g_swinl_c3", "g_swinl_c5", "g_swinl_small_trained", "g_swinl_odd_trained"])
 def test_plugin_forward_exact_split_mode(case, parity_log):
     """The Swin goldens again with `fp8_corrections = False`: the exact 3-pass fp16 split everywhere (the round-1 path)."""
     g, m, out = _run_plugin(case, fp8=False)

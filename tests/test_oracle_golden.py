@@ -11,7 +11,7 @@ TOL_Z = 5e-5  # fp32-vs-fp32 re-association noise on the logits (SURVEY.md §7.2
 
 
 @pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small", "g_mpvit_trained", "g_res18_trained",
-                                  "g_swinl_small_trained"])
+                                  "g_swinl_small_trained", "g_swinl_odd_trained"])
 def test_oracle_reproduces_reference_golden(case):
     """`*_trained`: the trained-like regime (oracle.configs.trainedify: random non-zero Swin relative-position tables,
     non-trivial BatchNorm running statistics, LayerNorm / GroupNorm affines) — what released checkpoints look like."""
@@ -39,7 +39,7 @@ def test_oracle_reproduces_reference_golden(case):
 
 
 @pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small", "g_mpvit_trained", "g_res18_trained",
-                                  "g_swinl_small_trained"])
+                                  "g_swinl_small_trained", "g_swinl_odd_trained"])
 def test_mirror_producers_match_reference_condition(case):
     """backbone + FPN of the product mirror (torch ops, once per image) reproduce the reference's cond map."""
     g = helpers.load_golden(case)
