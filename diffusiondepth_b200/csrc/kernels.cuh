@@ -408,7 +408,15 @@ __device__ __forceinline__ void ldv_stream(const float* p, float (&v)[V]) {
 template <int V, int QPB>  // QPB quads (consecutive quad columns) per block of QPB * 256 / V threads
 __global__ void __launch_bounds__(QPB * 256 / V, 12 / QPB) gn_apply_up_split_kernel(const ApplyArgs a) {
   constexpr int C = 256, TPQ = C / V;
+  // Blocks are dispatched in increasing (z, y, x); this kernel walks the images and quad rows BACKWARDS (DD_UP_FORWARD: A/B
+  // build): its producer (the persistent 64 -> 256 conv, tiles in increasing order) has just written the END of the conv
+  // output, which is what still sits in the 126 MB L2, and its consumer (convA, tiles in increasing order) starts with what
+  // this kernel wrote LAST.
+#ifdef DD_UP_FORWARD
   const int b = blockIdx.z, qy = blockIdx.y;
+#else
+  const int b = gridDim.z - 1 - blockIdx.z, qy = gridDim.y - 1 - blockIdx.y;
+#endif
   const int qx = QPB == 1 ? blockIdx.x : blockIdx.x * QPB + threadIdx.x / TPQ;  // quad q: output columns {2q - 1, 2q} in [0, W)
   if (QPB > 1 && qx > a.W / 2) return;
   const int c0 = (threadIdx.x % TPQ) * V;
