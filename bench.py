@@ -197,9 +197,18 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL prints its "NCCL version ..." banner with printf when the communicator is
+        # created (NCCL_DEBUG=VERSION on the pool's boxes), so file descriptor 1 points at stderr while that happens
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()  # eager communicator creation: the banner is out before stdout comes back
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     model = dd_helpers.build_mirror(family, T).to(dev)
     model.depth_head.use_cuda_graph = not args.no_graph
     model.depth_head.check_range = False
