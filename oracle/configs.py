@@ -14,6 +14,10 @@ FAMILIES = {
                       head_specify="DDIMDepthEstimate_Swin_ADD"),
     "mpvit_s": dict(backbone_module="mpvit", backbone_name="mpvit_small",
                     head_specify="DDIMDepthEstimate_MPVIT_ADDHAHI"),
+    # the `*Vis` heads: same loop, `pred_inter` = the depth map decoded after EVERY step
+    "res18_vis": dict(backbone_module="mmbev_resnet", backbone_name="mmbev_res18", head_specify="DDIMDepthEstimate_ResVis"),
+    "swinl_vis": dict(backbone_module="swin", backbone_name="swin_large_naive_nopretrain",
+                      head_specify="DDIMDepthEstimate_Swin_ADDHAHIVis"),
 }
 
 # name -> (family, T, batch, H, W).  C1..C5 = BASELINE.json configs[0..4]
@@ -50,6 +54,9 @@ GOLDEN_TRAINED = {
     # ratio exactly 0.5 but NOT the 2x layout: half of the outputs of the quad-based condition-injection kernel take their
     # per-tap path), every pyramid level odd (18x27, 9x14, 5x7, 3x4: resampling FPN, padded + shifted windows)
     "g_swinl_odd_trained": ("swinl", 5, 2, 70, 106),
+    # `*Vis` heads (reference ..._res_vis.py / ..._swin_addHAHI_vis.py): the golden also holds `pred_inter` [T, B, 1, H, W]
+    "g_res18_vis_trained": ("res18_vis", 5, 2, 70, 106),
+    "g_swinl_vis_trained": ("swinl_vis", 5, 1, 96, 160),
 }
 SEED_TRAINED = 99
 

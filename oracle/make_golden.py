@@ -76,6 +76,8 @@ def generate(case):
         arr, stride = subsample(name, r[name], H, W)
         arrays[name] = arr.numpy()
         arrays[name + "_stride"] = np.int32(stride)
+    if "pred_inter" in r:
+        arrays["pred_inter"] = r["pred_inter"].float().numpy()
     z = r["logits"].double()
     arrays.update(
         meta=np.array([T, B, H, W], dtype=np.int32), family=np.array(family),

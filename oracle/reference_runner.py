@@ -50,5 +50,8 @@ def run_reference(net, sample, noise):
     finally:
         for h in hooks:
             h.remove()
-    return dict(pred=out["pred"], logits=cap["logits"], latent=cap["latent"], cond=cap["cond"],
-                pred_init=out["pred_init"], keys=sorted(out.keys()))
+    r = dict(pred=out["pred"], logits=cap["logits"], latent=cap["latent"], cond=cap["cond"],
+             pred_init=out["pred_init"], keys=sorted(out.keys()))
+    if out.get("pred_inter") is not None:  # the `*Vis` heads: one decoded map per DDIM step
+        r["pred_inter"] = torch.stack([p.detach() for p in out["pred_inter"]])
+    return r

@@ -11,7 +11,7 @@ TOL_Z = 5e-5  # fp32-vs-fp32 re-association noise on the logits (SURVEY.md §7.2
 
 
 @pytest.mark.parametrize("case", ["g_res18_c1", "g_res18_ragged", "g_mpvit_small", "g_mpvit_trained", "g_res18_trained",
-                                  "g_swinl_small_trained", "g_swinl_odd_trained"])
+                                  "g_swinl_small_trained", "g_swinl_odd_trained", "g_res18_vis_trained"])
 def test_oracle_reproduces_reference_golden(case):
     """`*_trained`: the trained-like regime (oracle.configs.trainedify: random non-zero Swin relative-position tables,
     non-trivial BatchNorm running statistics, LayerNorm / GroupNorm affines) — what released checkpoints look like."""
